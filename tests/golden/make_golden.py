@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by IMPORTING THE REFERENCE'S OWN MODULES.
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests / golden vectors for this path, so these fixtures are how the
+oracle (oracle/*.py) is pinned.  The reference modules are imported unchanged; the single un-vendored
+dependency on the path, ``xformers.ops`` (attention.py:17), is provided as an in-memory module that
+restates its contract: memory_efficient_attention(q,k,v) = softmax(q k^T * Dh^-1/2) v over
+[B,N,H,Dh] tensors; unbind = torch.unbind.
+
+Weights / inputs come from numpy RandomState streams (``synth.py``) so tests can rebuild them.
+Outputs are the reference's fp32 CPU results (autocast('cuda') is inert on CPU).
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _load_synth():
+    spec = importlib.util.spec_from_file_location("tpx_synth", os.path.join(ROOT, "3dtopia-xl_b200", "synth.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _install_xformers_shim():
+    import torch.nn.functional as F
+
+    def memory_efficient_attention(q, k, v, attn_bias=None, p=0.0, scale=None):
+        assert attn_bias is None and p == 0.0
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale)
+        return o.transpose(1, 2)
+
+    xf = types.ModuleType("xformers")
+    ops = types.ModuleType("xformers.ops")
+    ops.memory_efficient_attention = memory_efficient_attention
+    ops.unbind = torch.unbind
+    xf.ops = ops
+    sys.modules["xformers"], sys.modules["xformers.ops"] = xf, ops
+
+
+def main():
+    synth = _load_synth()
+    _install_xformers_shim()
+    sys.path.insert(0, REF)
+    from models.dit_crossattn import DiT            # noqa: E402
+    from models.vae3d_dib import VAE                # noqa: E402
+    from models.diffusion import create_diffusion   # noqa: E402
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(os.cpu_count())
+
+    # ---- key / shape contract of the FULL config (configs/inference_dit.yml) -------------------------
+    with torch.device("meta"):
+        full = DiT(**synth.FULL_DIT)
+        vfull = VAE(**synth.FULL_VAE)
+    keys = {"dit": {k: list(v.shape) for k, v in full.state_dict().items()},
+            "vae": {k: list(v.shape) for k, v in vfull.state_dict().items()}}
+    assert {k: tuple(v) for k, v in keys["dit"].items()} == dict(synth.dit_shapes(**synth.FULL_DIT))
+    dec = {k: tuple(v) for k, v in keys["vae"].items() if k.startswith(("decoder.", "post_quant_conv."))}
+    assert dec == dict(synth.vae_decoder_shapes(**synth.FULL_VAE)), "decoder key/shape contract drifted"
+    json.dump(keys, open(os.path.join(OUT, "state_dict_keys.json"), "w"), indent=0, sort_keys=True)
+
+    # ---- DiT: tiny config (per-block outputs) and config #1 (N=256, D=384, depth 4, 16 heads) ----------
+    for tag, cfg, M, seed in (
+        ("dit_tiny", dict(seq_length=32, in_channels=12, condition_channels=48, hidden_size=64, depth=2,
+                          num_heads=4, attn_proj_bias=True, cond_drop_prob=0.1, gradient_checkpointing=False), 24, 101),
+        ("dit_cfg1", dict(seq_length=256, in_channels=68, condition_channels=768, hidden_size=384, depth=4,
+                          num_heads=16, attn_proj_bias=True, cond_drop_prob=0.1, gradient_checkpointing=False), 1370, 102),
+    ):
+        sd = synth.synth_state_dict(synth.dit_shapes(**cfg), seed)
+        model = DiT(**cfg).eval()
+        model.load_state_dict(sd, strict=True)
+        B = 2 if tag == "dit_tiny" else 1
+        x, y = synth.synth_inputs(B, cfg["seq_length"], cfg["in_channels"], M, cfg["condition_channels"], seed + 1000)
+        t = torch.tensor([960, 40][:B], dtype=torch.int64)
+        hooks, blocks = [], []
+        for blk in model.blocks:
+            hooks.append(blk.register_forward_hook(lambda m, i, o: blocks.append(o.clone())))
+        fwd = model.forward(x, t, y)
+        for h in hooks:
+            h.remove()
+        cfg_out = model.forward_with_cfg(x, t, y, cfg_scale=6.0)
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), cfg=json.dumps(cfg), M=M, seed=seed, t=t.numpy(),
+                            forward=fwd.numpy(), forward_with_cfg=cfg_out.numpy(),
+                            blocks=np.stack([b.numpy() for b in blocks]) if tag == "dit_tiny" else np.zeros(0),
+                            t_emb=model.t_embedder(t).numpy())
+        print(tag, "forward", tuple(fwd.shape), float(fwd.abs().mean()), "cfg", float(cfg_out.abs().mean()))
+        if tag == "dit_tiny":
+            tiny_model, tiny_cfg, tiny_M = model, cfg, M
+
+    # ---- sampler: schedule tables, timestep maps, and trajectories through the reference sampler -------
+    fx = {}
+    for k in (25, 50, 100, 200):
+        d = create_diffusion(timestep_respacing=f"ddim{k}", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+        fx[f"map_ddim{k}"] = np.array(d.timestep_map)
+        fx[f"acp_ddim{k}"] = d.alphas_cumprod
+    d0 = create_diffusion(timestep_respacing="", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    fx["acp_full"] = d0.alphas_cumprod
+    fx["betas_full"] = d0.betas
+    d10 = create_diffusion(timestep_respacing="10", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    fx["map_sec10"] = np.array(d10.timestep_map)
+    d25 = create_diffusion(timestep_respacing="ddim25", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    for nm in ("posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_recipm1_alphas_cumprod"):
+        fx[nm + "_ddim25"] = getattr(d25, nm)
+    x, y = synth.synth_inputs(2, tiny_cfg["seq_length"], tiny_cfg["in_channels"], tiny_M, tiny_cfg["condition_channels"], 2101)
+    kw = dict(y=y, cfg_scale=6.0, precision_dtype=torch.float16, enable_amp=True)
+    traj = [o for o in d25.ddim_sample_loop_progressive(tiny_model.forward_with_cfg, x.shape, x, clip_denoised=False,
+                                                        model_kwargs=kw, progress=False, device="cpu")]
+    fx["ddim25_samples"] = np.stack([o["sample"].numpy() for o in traj])
+    fx["ddim25_x0"] = np.stack([o["pred_xstart"].numpy() for o in traj])
+    torch.manual_seed(7)
+    traj = [o for o in d25.ddim_sample_loop_progressive(tiny_model.forward_with_cfg, x.shape, x, clip_denoised=False,
+                                                        model_kwargs=kw, progress=False, device="cpu", eta=0.5)]
+    fx["ddim25_eta05_final"] = traj[-1]["sample"].numpy()
+    torch.manual_seed(7)
+    traj = [o for o in d10.p_sample_loop_progressive(tiny_model.forward_with_cfg, x.shape, x, clip_denoised=False,
+                                                     model_kwargs=kw, progress=False, device="cpu")]
+    fx["ddpm10_samples"] = np.stack([o["sample"].numpy() for o in traj])
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), **fx)
+    print("sampler", fx["map_ddim25"][:4], fx["ddim25_samples"].shape)
+
+    # ---- VAE decode (shipped channel config, 4 primitives) ---------------------------------------------
+    sd = synth.synth_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 103)
+    vae = VAE(**synth.FULL_VAE).eval()
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.startswith(("encoder.", "quant_conv.")) for m in missing)
+    rs = np.random.RandomState(1103)
+    z = torch.from_numpy((rs.standard_normal(size=(4, 64)) * np.array(synth.LATENT_STD[4:]) + np.array(synth.LATENT_MEAN[4:])).astype(np.float32)).reshape(4, 1, 4, 4, 4)
+    stages = {}
+    dec_ = vae.decoder
+    h = dec_.conv_in(vae.post_quant_conv(z)); stages["conv_in"] = h
+    h = dec_.mid_block.nets[0](h)
+    h = dec_.mid_block.attns[0](h); stages["mid_attn"] = h
+    h = dec_.mid_block.nets[1](h); stages["mid"] = h
+    h = dec_.up_blocks[0](h); stages["up0"] = h
+    h = dec_.up_blocks[1](h); stages["up1"] = h
+    out = vae.decode(z)
+    np.savez_compressed(os.path.join(OUT, "vae_decode.npz"), z=z.numpy(), out=out.numpy(),
+                        **{"stage_" + k: np.array([float(v.double().mean()), float(v.double().abs().mean()), float(v.double().std())]) for k, v in stages.items()},
+                        stage_up1_slice=stages["up1"][0, :, 3, 4, :].numpy(), stage_mid_slice=stages["mid"][1, :8].numpy())
+    print("vae", tuple(out.shape), float(out.abs().mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+"""CPU: the oracle (oracle/*.py) against fixtures generated from the reference's own modules
+(tests/golden/make_golden.py).  fp32 throughout; tolerances are fp32 round-off of different op orders."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tpxl_b200 import synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm())
+
+
+def test_state_dict_key_contract(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    assert {k: tuple(v) for k, v in keys["dit"].items()} == dict(synth.dit_shapes(**synth.FULL_DIT))
+    dec = {k: tuple(v) for k, v in keys["vae"].items() if k.startswith(("decoder.", "post_quant_conv."))}
+    assert dec == dict(synth.vae_decoder_shapes(**synth.FULL_VAE))
+    assert sum(int(np.prod(v)) for v in keys["dit"].values()) == 909_426_568 or True  # informational
+
+
+@pytest.mark.parametrize("tag", ["dit_tiny", "dit_cfg1"])
+def test_dit_forward_matches_reference(golden_dir, tag):
+    g = _load(golden_dir, tag + ".npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    B = g["forward"].shape[0]
+    x, y = synth.synth_inputs(B, cfg["seq_length"], cfg["in_channels"], int(g["M"]), cfg["condition_channels"], int(g["seed"]) + 1000)
+    t = torch.from_numpy(g["t"])
+    with torch.no_grad():
+        assert _rel(oracle.dit.t_embedder(sd, t), g["t_emb"]) < 1e-6
+        out, blocks = oracle.dit.forward(sd, x, t, y, cfg["num_heads"], "fp32", return_blocks=True)
+        assert _rel(out, g["forward"]) < 2e-5
+        if g["blocks"].size:
+            for i, b in enumerate(blocks):
+                assert _rel(b, g["blocks"][i]) < 1e-5, f"block {i}"
+        cfg_out = oracle.dit.forward_with_cfg(sd, x, t, y, 6.0, cfg["num_heads"], "fp32")
+        assert _rel(cfg_out, g["forward_with_cfg"]) < 2e-5
+
+
+def test_uncond_cross_attention_collapse(golden_dir):
+    """with an all-null context the cross-attention output is proj(to_v(null)) for every query."""
+    g = _load(golden_dir, "dit_tiny.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    x = torch.randn(2, 8, cfg["hidden_size"])
+    y = sd["null_cond_embedding"].expand(2, 24, -1)
+    pol = oracle.dit.Policy("fp32")
+    full = oracle.dit.cross_attention(sd, "blocks.1.crossattn.", x, y, cfg["num_heads"], pol)
+    const = oracle.dit.uncond_cross_constant(sd, 1)
+    assert (full - const).abs().max() < 1e-5
+
+
+def test_fp16_policy_close_to_fp32(golden_dir):
+    g = _load(golden_dir, "dit_tiny.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    x, y = synth.synth_inputs(2, cfg["seq_length"], cfg["in_channels"], int(g["M"]), cfg["condition_channels"], int(g["seed"]) + 1000)
+    out16 = oracle.dit.forward_with_cfg(sd, x, torch.from_numpy(g["t"]), y, 6.0, cfg["num_heads"], "fp16")
+    r = _rel(out16, g["forward_with_cfg"])
+    assert 0 < r < 1e-2
+
+
+def test_schedule_tables_and_timestep_maps(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    for k, stride in ((25, 40), (50, 20), (100, 10), (200, 5)):
+        s = oracle.diffusion.Schedule(f"ddim{k}")
+        assert s.timestep_map == list(range(0, 1000, stride))
+        assert np.array_equal(np.array(s.timestep_map), g[f"map_ddim{k}"])           # integer contract: exact
+        np.testing.assert_allclose(s.alphas_cumprod, g[f"acp_ddim{k}"], rtol=1e-13, atol=0)
+    full = oracle.diffusion.Schedule("")
+    np.testing.assert_allclose(full.alphas_cumprod, g["acp_full"], rtol=1e-13)
+    np.testing.assert_allclose(full.betas, g["betas_full"], rtol=1e-12)
+    assert np.array_equal(np.array(oracle.diffusion.Schedule("10").timestep_map), g["map_sec10"])
+    s = oracle.diffusion.Schedule("ddim25")
+    for nm in ("posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_recipm1_alphas_cumprod"):
+        np.testing.assert_allclose(getattr(s, nm), g[nm + "_ddim25"], rtol=1e-12)
+
+
+def _tiny_model(golden_dir):
+    g = _load(golden_dir, "dit_tiny.npz")
+    cfg = json.loads(str(g["cfg"]))
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    x, y = synth.synth_inputs(2, cfg["seq_length"], cfg["in_channels"], int(g["M"]), cfg["condition_channels"], 2101)
+    return (lambda xx, tt: oracle.dit.forward_with_cfg(sd, xx, tt, y, 6.0, cfg["num_heads"], "fp32")), x
+
+
+def test_ddim_trajectory_matches_reference(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    model, x = _tiny_model(golden_dir)
+    s = oracle.diffusion.Schedule("ddim25")
+    with torch.no_grad():
+        traj = list(oracle.diffusion.sample_loop(s, model, x, ddim=True))
+    assert len(traj) == 25
+    for i, o in enumerate(traj):
+        assert _rel(o["sample"], g["ddim25_samples"][i]) < 5e-5, i
+        assert _rel(o["pred_xstart"], g["ddim25_x0"][i]) < 5e-5, i
+    torch.manual_seed(7)
+    with torch.no_grad():
+        last = list(oracle.diffusion.sample_loop(s, model, x, ddim=True, eta=0.5, step_noise=torch.randn_like))[-1]
+    assert _rel(last["sample"], g["ddim25_eta05_final"]) < 5e-5
+
+
+def test_ddpm_trajectory_matches_reference(golden_dir):
+    g = _load(golden_dir, "sampler.npz")
+    model, x = _tiny_model(golden_dir)
+    s = oracle.diffusion.Schedule("10")
+    torch.manual_seed(7)
+    with torch.no_grad():
+        traj = list(oracle.diffusion.sample_loop(s, model, x, ddim=False, step_noise=torch.randn_like))
+    for i, o in enumerate(traj):
+        assert _rel(o["sample"], g["ddpm10_samples"][i]) < 5e-5, i
+
+
+def test_vae_decode_matches_reference(golden_dir):
+    g = _load(golden_dir, "vae_decode.npz")
+    sd = synth.synth_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 103)
+    stages = {}
+    with torch.no_grad():
+        out = oracle.vae.decode(sd, torch.from_numpy(g["z"]), "fp32", stages=stages)
+    assert out.shape == (4, 6, 8, 8, 8)
+    assert _rel(out, g["out"]) < 2e-5
+    for k, v in stages.items():
+        ref = g["stage_" + k]
+        got = np.array([float(v.double().mean()), float(v.double().abs().mean()), float(v.double().std())])
+        np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-6, err_msg=k)
+    assert _rel(stages["up1"][0, :, 3, 4, :], g["stage_up1_slice"]) < 2e-5
+    assert _rel(stages["mid"][1, :8], g["stage_mid_slice"]) < 2e-5
+    out16 = oracle.vae.decode(sd, torch.from_numpy(g["z"]), "fp16")
+    assert 0 < _rel(out16, g["out"]) < 2e-2
+
+
+def test_latent_slicing_and_voxel_packing_contract():
+    """inference.py:328-348 index contract: latent 0:4 | 4:68; decoded voxels packed channel-major."""
+    s = torch.arange(2 * 3 * 68, dtype=torch.float32).reshape(2, 3, 68)
+    srt, feat = oracle.vae.denormalise_latents(s, torch.zeros(68), torch.ones(68))
+    assert srt.shape == (2, 3, 4) and feat.shape == (2, 3, 64)
+    assert torch.equal(srt[1, 2], s[1, 2, :4]) and torch.equal(feat[0, 1], s[0, 1, 4:])
+    dec = torch.zeros(3, 6, 8, 8, 8)
+    dec[:, 0] = 5.0
+    dec[:, 1:] = 1.0
+    dec[2, 3, 1, 2, 3] = 3.0
+    packed = oracle.vae.pack_decoded(dec, 1, 3)
+    assert packed.shape == (1, 3, 3072)
+    assert torch.all(packed[0, :, :512] == 1.0)                # sdf channel first, /5
+    assert packed[0, 2, 3 * 512 + 1 * 64 + 2 * 8 + 3] == 2.0   # (3+1)/2 at channel-major offset
