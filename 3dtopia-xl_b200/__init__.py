@@ -1,4 +1,33 @@
-"""B200-native denoising hot path for 3DTopia-XL (DiT + DDIM/CFG + VAE decode).  See DESIGN.md."""
+"""B200-native denoising hot path for 3DTopia-XL: DiT step (CFG x2) + DDIM/DDPM update + VAE decode.
+
+Python host layer = the reference's own interfaces (``DiT``, ``create_diffusion``, ``VAE``) calling the
+sm_100a kernels in ``lib/libtpx_b200.so`` through the C ABI of ``include/tpx.h``.  See DESIGN.md and
+INTEGRATION.md.  There is no CPU or other-architecture fallback anywhere in this package.
+"""
+import sys
+import types
+
 from . import synth  # noqa: F401
+from . import _lib  # noqa: F401
+from . import diffusion, dit, vae  # noqa: F401
+from .diffusion import SpacedDiffusion, create_diffusion  # noqa: F401
+from .dit import DiT  # noqa: F401
+from .vae import VAE  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def install() -> None:
+    """Make the reference's import paths resolve to this implementation, so ``inference.py`` / ``app.py`` run
+    unchanged:  ``models.dit_crossattn`` -> dit, ``models.vae3d_dib`` -> vae, ``models.diffusion`` -> diffusion.
+    (Equivalent to editing ``class_name`` in configs/inference_dit.yml:32,53; see INTEGRATION.md.)  If the reference's
+    ``models`` package is importable it is imported first so its other members (conditioner, primsdf) keep working."""
+    try:
+        import models as ref_models  # the reference checkout, when it is on sys.path
+    except Exception:
+        ref_models = types.ModuleType("models")
+        ref_models.__path__ = []
+        sys.modules["models"] = ref_models
+    for name, mod in (("dit_crossattn", dit), ("vae3d_dib", vae), ("diffusion", diffusion)):
+        sys.modules["models." + name] = mod
+        setattr(ref_models, name, mod)

@@ -1,0 +1,176 @@
+// Host launcher for the tcgen05 GEMM: tensor-map construction (cached), tile-shape dispatch.
+#include "gemm_tc.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace tpx {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return TPX_ERR_CUDA;
+}
+
+int gemm_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
+
+using MapKey = std::tuple<const void*, long long, long long, long long, int, int, int>;
+static std::map<MapKey, CUtensorMap> g_maps;
+static std::mutex g_maps_mu;
+
+// 2-D: row-major [rows, K] fp16, box = [box_rows, bk]
+static int map_2d(const void* ptr, long long rows, long long K, long long ld, int box_rows, int bk, CUtensorMap* out) {
+    MapKey key{ptr, rows, K, ld, box_rows, bk, 2};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return TPX_OK; }
+    EncodeTiledFn enc = encode_fn();
+    TPX_CHECK(enc != nullptr, TPX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+    TPX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, TPX_ERR_ARG, "TMA operand must be 16-B aligned (ptr %p ld %lld)", ptr, ld);
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TPX_CHECK(r == CUDA_SUCCESS, TPX_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (rows %lld K %lld ld %lld box %d x %d)", (int)r, rows, K, ld, box_rows, bk);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+    *out = m;
+    return TPX_OK;
+}
+
+// 5-D: channels-last volume [P, S, S, S, C] fp16; box = 128 voxel rows x bk channels
+static int map_conv(const void* ptr, long long P, int S, int C, int bk, CUtensorMap* out) {
+    MapKey key{ptr, P, S, C, 0, bk, 5};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return TPX_OK; }
+    EncodeTiledFn enc = encode_fn();
+    TPX_CHECK(enc != nullptr, TPX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+    TPX_CHECK(S == 4 || S == 8, TPX_ERR_SHAPE, "conv volume edge must be 4 or 8, got %d", S);
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)P};
+    cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)S * C * 2, (cuuint64_t)S * S * C * 2, (cuuint64_t)S * S * S * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)S, (cuuint32_t)S, (cuuint32_t)(S == 4 ? 4 : 2), (cuuint32_t)(S == 4 ? 2 : 1)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TPX_CHECK(r == CUDA_SUCCESS, TPX_ERR_CUDA, "cuTensorMapEncodeTiled(5d) failed: %d (P %lld S %d C %d bk %d)", (int)r, P, S, C, bk);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+    *out = m;
+    return TPX_OK;
+}
+
+template <int BN, int BK, int AMODE, int EPI>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, BK>;
+    auto kern = gemm_tc_kernel<BN, BK, AMODE, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((a.M + 127) / 128) * ((a.N + BN - 1) / BN);
+    const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
+int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
+    TPX_CHECK(p.M > 0 && p.N > 0 && p.K > 0, TPX_ERR_SHAPE, "gemm: empty problem %d x %d x %d", p.M, p.N, p.K);
+    TPX_CHECK(p.N % 8 == 0 && p.K % 8 == 0, TPX_ERR_SHAPE, "gemm: N (%d) and K (%d) must be multiples of 8", p.N, p.K);
+    const int bk = (p.a_mode == AMODE_CONV3 && p.conv_C == 32) ? 32 : 64;
+    GemmArgs a = p.args;
+    a.M = p.M;
+    a.N = p.N;
+    a.num_kb = (p.K + bk - 1) / bk;
+    a.conv_S = p.conv_S;
+    a.chunks_per_tap = p.a_mode == AMODE_CONV3 ? p.conv_C / bk : 1;
+    CUtensorMap ta, tb;
+    int rc;
+    if (p.a_mode == AMODE_LINEAR) {
+        rc = map_2d(p.A, p.M, p.K, p.lda, 128, bk, &ta);
+    } else {
+        TPX_CHECK(p.conv_C % bk == 0 && p.K == 27 * p.conv_C, TPX_ERR_SHAPE, "conv gemm: K (%d) must be 27*C (%d)", p.K, p.conv_C);
+        const int s3 = p.conv_S * p.conv_S * p.conv_S;
+        TPX_CHECK(p.M % s3 == 0, TPX_ERR_SHAPE, "conv gemm: M (%d) must be P*S^3", p.M);
+        rc = map_conv(p.A, p.M / s3, p.conv_S, p.conv_C, bk, &ta);
+    }
+    if (rc != TPX_OK) return rc;
+    rc = map_2d(p.W, p.N, p.K, p.K, p.BN, bk, &tb);
+    if (rc != TPX_OK) return rc;
+
+#define TPX_CASE(BN_, BK_, AM_, EP_) \
+    if (p.BN == BN_ && bk == BK_ && p.a_mode == AM_ && p.epi == EP_) return launch_one<BN_, BK_, AM_, EP_>(ta, tb, a, stream);
+    // DiT (every tile width x every DiT epilogue, so any hidden size that is a multiple of 128 works)
+    TPX_CASE(128, 64, AMODE_LINEAR, EPI_STORE)
+    TPX_CASE(128, 64, AMODE_LINEAR, EPI_GELU)
+    TPX_CASE(128, 64, AMODE_LINEAR, EPI_HEADS)
+    TPX_CASE(128, 64, AMODE_LINEAR, EPI_GATED)
+    TPX_CASE(192, 64, AMODE_LINEAR, EPI_STORE)
+    TPX_CASE(192, 64, AMODE_LINEAR, EPI_GELU)
+    TPX_CASE(192, 64, AMODE_LINEAR, EPI_HEADS)
+    TPX_CASE(192, 64, AMODE_LINEAR, EPI_GATED)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_STORE)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_GELU)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_HEADS)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_GATED)
+    // VAE
+    TPX_CASE(256, 64, AMODE_CONV3, EPI_STORE)
+    TPX_CASE(256, 64, AMODE_CONV3, EPI_RESID_SCALE)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_RESID_SCALE)
+    TPX_CASE(256, 64, AMODE_LINEAR, EPI_CONVT2)
+    TPX_CASE(32, 64, AMODE_CONV3, EPI_STORE)
+    TPX_CASE(32, 64, AMODE_LINEAR, EPI_STORE)
+    TPX_CASE(32, 32, AMODE_CONV3, EPI_STORE)
+    TPX_CASE(32, 32, AMODE_CONV3, EPI_RESID_SCALE)
+    TPX_CASE(16, 32, AMODE_CONV3, EPI_NCDHW)
+#undef TPX_CASE
+    set_error("gemm: no kernel instantiated for BN=%d BK=%d amode=%d epi=%d", p.BN, bk, p.a_mode, p.epi);
+    return TPX_ERR_SHAPE;
+}
+
+}  // namespace tpx

@@ -1,0 +1,40 @@
+// Internal launcher declarations shared by the translation units of libtpx_b200.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace tpx {
+
+struct SamplerCoefs {
+    float sqrt_ab, sqrt_1mab, sqrt_recip_ab, sqrt_recipm1_ab;  // _extract_into_tensor(...)[t] as fp32
+    float c_x0, c_eps, sigma, nonzero;                           // DDIM: sqrt(ab_prev), sqrt(1-ab_prev-sigma^2), sigma, (t != 0)
+    float coef1, coef2, min_log, max_log;                        // DDPM: posterior mean coefs, log-variance range
+    int clip;
+};
+
+const char* last_error();
+
+// elementwise.cu
+int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift, const __half* scale, int mod_bstride, int rows_per_batch,
+                       int mod_batches, __half* out, const __half* pre_gate, const __half* pre_const, int pre_row0, cudaStream_t st);
+enum { GEMV_IN_TIMESTEP = 0, GEMV_IN_F32 = 1, GEMV_IN_F16 = 2 };
+enum { GEMV_OUT_F32 = 0, GEMV_OUT_F32_SILU = 1, GEMV_OUT_F16 = 2, GEMV_OUT_F32_AND_SILU16 = 3 };
+int launch_gemv(int in_mode, int out_mode, const __half* W, const __half* bias, const void* in, const long long* t, int B, int J, int K, void* out,
+                __half* out2, int out_ld, cudaStream_t st);
+int launch_x_embed(const float* x, const __half* W, const __half* bias, int rows, int Cin, int D, float* out, long long dup_offset, cudaStream_t st);
+int launch_cfg_combine(const __half* both, long long n_half, float s, __half* out, cudaStream_t st);
+int launch_sampler_step(int ddim, const float* x, const void* mo, int mo_is_half, const float* noise, long long n, int C, const SamplerCoefs& k,
+                        float* x_prev, float* x0_out, cudaStream_t st);
+int launch_to_half(const void* src, int src_dtype, __half* dst, long long n, cudaStream_t st);
+int launch_fill_rows_half(const __half* vec, __half* dst, long long rows, int K, cudaStream_t st);
+
+// attention.cu :  q [B,H,Nq,DhP], k/v [B,H,Nk,DhP] fp16 (zero padded beyond Dh) -> out [B,Nq,H*Dh] fp16
+int launch_attention(const __half* q, const __half* k, const __half* v, __half* out, int B, int H, int Nq, int Nk, int Dh, int DhP, float scale,
+                     cudaStream_t st);
+
+// vae_kernels.cu
+int launch_vae_conv_in(const void* z, int z_dtype, const __half* w_pq, const __half* b_pq, const __half* W, const __half* bias, int P, int C,
+                       __half* out, cudaStream_t st);
+int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* beta, int P, int S3, int C, int groups, float eps, int apply_silu,
+                          __half* out, cudaStream_t st);
+
+}  // namespace tpx

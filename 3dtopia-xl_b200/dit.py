@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's DiT interface, backed by libtpx_b200 (sm_100a kernels).
+
+Drop-in for ``models.dit_crossattn.DiT`` (/root/reference/models/dit_crossattn.py:111-213): same
+constructor kwargs (configs/inference_dit.yml:52-62), same ``load_state_dict`` key names, same
+``forward`` / ``forward_with_cfg`` signatures, so ``inference.py`` / ``app.py`` and the reference's own
+sampler can call it unchanged.  All compute is CUDA; there is no CPU path.
+
+What is different underneath (results stay within the fp16 tolerance of the reference, tests/):
+  * parameters live once, as fp16, in a packed store owned by the C library (the reference keeps fp32
+    modules and lets autocast re-cast ~905 M weights every forward);
+  * cross-attention K/V of all blocks are computed once per conditioning tensor ``y`` and cached
+    (keyed on the tensor's storage pointer + version counter), not once per step;
+  * under ``forward_with_cfg`` the null-conditioned half of the batch does not run cross-attention at
+    all: with an all-equal context the softmax is uniform and the branch equals a per-block constant.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, Iterator, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .synth import dit_shapes
+
+
+class DiT(nn.Module):
+    def __init__(self, seq_length=2, in_channels=4, condition_channels=512, hidden_size=1152, depth=28, num_heads=16,
+                 mlp_ratio=4.0, cond_drop_prob=0.0, attn_proj_bias=False, learn_sigma=True, gradient_checkpointing=False):
+        super().__init__()
+        self.gradient_checkpointing = gradient_checkpointing
+        self.learn_sigma = learn_sigma
+        self.in_channels = in_channels
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.seq_length = seq_length
+        self.num_heads = num_heads
+        self.cond_drop_prob = cond_drop_prob
+        self.hidden_size = hidden_size
+        self.depth = depth
+        self.condition_channels = condition_channels
+        self.mlp_hidden = int(hidden_size * mlp_ratio)
+        self._shapes = dit_shapes(in_channels=in_channels, condition_channels=condition_channels, hidden_size=hidden_size, depth=depth,
+                                  mlp_ratio=mlp_ratio, attn_proj_bias=attn_proj_bias, cond_drop_prob=cond_drop_prob, learn_sigma=learn_sigma)
+        # one tiny real parameter so `.to(device)`, `next(model.parameters()).device` (gaussian_diffusion.py:669) work
+        self._anchor = nn.Parameter(torch.zeros(1), requires_grad=False)
+        self._sd: Optional["OrderedDict[str, torch.Tensor]"] = None
+        self._handle = None
+        self._handle_device = None
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._cond_ws: Optional[torch.Tensor] = None
+        self._cond_key = None
+        self.collapse_null_branch = True     # set False to run the null half through real cross-attention (tests)
+
+    # ---- parameters: reference key names, values kept as given (CPU or GPU, fp16 or fp32) ----------------
+    def _default_init(self) -> "OrderedDict[str, torch.Tensor]":
+        """Same scheme as DiT.initialize_weights (dit_crossattn.py:158-182): xavier-uniform Linear weights, zero
+        biases, N(0, 0.02) timestep MLP, zero adaLN / output layers, N(0,1) null embedding."""
+        sd = OrderedDict()
+        for k, shp in self._shapes.items():
+            if k == "null_cond_embedding":
+                sd[k] = torch.randn(shp)
+            elif k.endswith(".bias") or "adaLN_modulation" in k or k.startswith("final_layer.linear"):
+                sd[k] = torch.zeros(shp)
+            elif k.startswith("t_embedder"):
+                sd[k] = torch.randn(shp) * 0.02
+            else:
+                bound = math.sqrt(6.0 / (shp[0] + shp[1]))
+                sd[k] = (torch.rand(shp) * 2 - 1) * bound
+        return sd
+
+    def state_dict(self, *args, **kwargs):
+        if self._sd is None:
+            self._sd = self._default_init()
+        return OrderedDict(self._sd)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing = [k for k in self._shapes if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._shapes]
+        errs = []
+        for k, shp in self._shapes.items():
+            if k in state_dict and tuple(state_dict[k].shape) != tuple(shp):
+                errs.append(f"size mismatch for {k}: copying a param with shape {tuple(state_dict[k].shape)}, expected {tuple(shp)}")
+        if strict and (missing or unexpected):
+            errs.append(f"Missing key(s): {missing[:5]}{'...' if len(missing) > 5 else ''}; unexpected key(s): {unexpected[:5]}")
+        if errs:
+            raise RuntimeError("Error(s) in loading state_dict for DiT:\n\t" + "\n\t".join(errs))
+        base = self._sd if self._sd is not None else (self._default_init() if missing else OrderedDict())
+        sd = OrderedDict()
+        for k in self._shapes:
+            sd[k] = state_dict[k].detach() if k in state_dict else base[k]
+        self._sd = sd
+        if self._handle is not None:
+            self._ingest()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        dev = self._anchor.device
+        if dev.type == "cuda" and (self._handle is None or self._handle_device != dev):
+            self._create_handle(dev)
+        return out
+
+    def _create_handle(self, dev: torch.device):
+        lib = _lib.lib()
+        self._destroy_handle()
+        cfg = _lib.DitConfig(self.seq_length, self.in_channels, self.out_channels, self.condition_channels, self.hidden_size, self.depth,
+                             self.num_heads, self.mlp_hidden)
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.tpx_dit_create(C.byref(cfg), C.byref(h)), "tpx_dit_create")
+        self._handle, self._handle_device = h, dev
+        self._ws.clear()
+        self._cond_ws, self._cond_key = None, None
+        self._ingest()
+
+    def _ingest(self):
+        lib = _lib.lib()
+        if self._sd is None:
+            self._sd = self._default_init()
+        dev = self._handle_device
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            keep = []
+            for k, v in self._sd.items():
+                t = v.detach()
+                if t.dtype not in (torch.float16, torch.float32):
+                    t = t.float()
+                t = t.to(dev, non_blocking=True).contiguous()
+                keep.append(t)
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.tpx_dit_set_weight(self._handle, k.encode(), t.data_ptr(), _lib.dtype_tag(t), shape, t.dim(), st), f"set_weight({k})")
+            _lib.check(lib.tpx_dit_finalize(self._handle, st), "tpx_dit_finalize")
+            torch.cuda.current_stream().synchronize()
+        self._cond_key = None
+
+    def _destroy_handle(self):
+        if self.__dict__.get("_handle") is not None:
+            try:
+                _lib.load_library().tpx_dit_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._destroy_handle()
+
+    # ---- forward -------------------------------------------------------------------------------------------
+    def _require_handle(self):
+        if self._handle is None:
+            raise _lib.TpxError("DiT is not on a CUDA device: call .to('cuda') first (this implementation has no CPU path)")
+
+    def _workspace(self, n_seq: int) -> torch.Tensor:
+        ws = self._ws.get(n_seq)
+        if ws is None:
+            nbytes = _lib.lib().tpx_dit_workspace_bytes(self._handle, n_seq)
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._handle_device)
+            self._ws[n_seq] = ws
+        return ws
+
+    @staticmethod
+    def _aligned(t: torch.Tensor) -> int:
+        return (t.data_ptr() + 255) & ~255
+
+    def _set_cond(self, y: torch.Tensor, with_null: bool):
+        """(Re)compute the hoisted cross-attention K/V when the conditioning tensor changed."""
+        key = (y.data_ptr(), y._version, tuple(y.shape), y.dtype, with_null)
+        if key == self._cond_key:
+            return
+        lib = _lib.lib()
+        yy = y.detach().to(self._handle_device, torch.float32).contiguous()
+        if with_null:
+            null = self._sd["null_cond_embedding"].to(self._handle_device, torch.float32)
+            yy = torch.cat([yy, null.expand_as(yy)], dim=0).contiguous()
+        n_cross, M = yy.shape[0], yy.shape[1]
+        nbytes = lib.tpx_dit_cond_bytes(self._handle, n_cross, M)
+        if self._cond_ws is None or self._cond_ws.numel() < nbytes + 256:
+            self._cond_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._handle_device)
+        _lib.check(lib.tpx_dit_set_cond(self._handle, yy.data_ptr(), n_cross, M, self._aligned(self._cond_ws), nbytes, _lib.stream_ptr()), "tpx_dit_set_cond")
+        self._cond_key = key
+
+    def _run(self, x, t, y, use_cfg: int, cfg_scale: float, enable_amp: bool):
+        self._require_handle()
+        if x.dim() != 3 or x.shape[1] != self.seq_length or x.shape[2] != self.in_channels:
+            raise ValueError(f"x must be [B,{self.seq_length},{self.in_channels}], got {tuple(x.shape)}")
+        if y.dim() != 3 or y.shape[0] != x.shape[0] or y.shape[2] != self.condition_channels:
+            raise ValueError(f"y must be [B,M,{self.condition_channels}] with B={x.shape[0]}, got {tuple(y.shape)}")
+        lib = _lib.lib()
+        dev = self._handle_device
+        with torch.cuda.device(dev):
+            B = x.shape[0]
+            xx = x.detach().to(dev, torch.float32).contiguous()
+            tt = t.detach().to(dev, torch.int64).contiguous()
+            if tt.shape != (B,):
+                raise ValueError(f"t must have shape [{B}], got {tuple(tt.shape)}")
+            self._set_cond(y, with_null=(use_cfg == 2))
+            n_seq = 2 * B if use_cfg else B
+            ws = self._workspace(n_seq)
+            out = torch.empty(B, self.seq_length, self.out_channels, dtype=torch.float16, device=dev)
+            nbytes = lib.tpx_dit_workspace_bytes(self._handle, n_seq)
+            _lib.check(lib.tpx_dit_forward(self._handle, xx.data_ptr(), tt.data_ptr(), B, use_cfg, float(cfg_scale), out.data_ptr(), self._aligned(ws),
+                                           nbytes, _lib.stream_ptr()), "tpx_dit_forward")
+        # the reference returns fp16 under autocast and fp32 otherwise (dit_crossattn.py:197-202)
+        return out if enable_amp else out.float()
+
+    def forward(self, x, t, y, precision_dtype=torch.float32, enable_amp=False):
+        """DiT.forward (dit_crossattn.py:184-202).  The kernels always compute in the reference's fp16-autocast
+        contract; with enable_amp=False the result is returned as fp32."""
+        return self._run(x, t, y, 0, 0.0, enable_amp)
+
+    def forward_with_cfg(self, x, t, y, cfg_scale=0.0, precision_dtype=torch.float32, enable_amp=False):
+        """DiT.forward_with_cfg (dit_crossattn.py:204-213)."""
+        if self.cond_drop_prob <= 0:
+            raise AttributeError("'DiT' object has no attribute 'null_cond_embedding'")   # as the reference would
+        return self._run(x, t, y, 1 if self.collapse_null_branch else 2, cfg_scale, enable_amp)
+
+    def debug_residual(self, n_seq: int) -> torch.Tensor:
+        """fp32 residual stream [n_seq, N, D] left by the last forward (parity tests)."""
+        self._require_handle()
+        out = torch.empty(n_seq, self.seq_length, self.hidden_size, dtype=torch.float32, device=self._handle_device)
+        _lib.check(_lib.lib().tpx_dit_debug_residual(self._handle, self._aligned(self._workspace(n_seq)), n_seq, out.data_ptr(), _lib.stream_ptr()))
+        return out

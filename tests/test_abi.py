@@ -1,0 +1,141 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports exactly what include/tpx.h declares; host-side
+logic (schedule, respacing, coefficient rounding, state_dict contract) works without a GPU; the compute path
+refuses to run without one."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tpxl_b200
+from tpxl_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__._load_build_module().build()
+    return _lib.load_library()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "tpx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tpx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/tpx.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert lib.tpx_version() == 100
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, "include", "tpx.h")).read()
+    for cite in ("dit_crossattn.py:184-202", "gaussian_diffusion.py", "vae3d_dib.py:437-440", "attention.py"):
+        assert cite in src
+
+
+def test_sass_contains_blackwell_tensor_and_tma_ops(lib):
+    """The GEMM really is tcgen05 + TMA (B200_PROFILING.md: UTCHMMA / UTMALDG / LDTM in SASS)."""
+    import subprocess
+    obj = os.path.join(ROOT, "3dtopia-xl_b200", "build", "gemm_tc.o")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem
+
+
+def test_compute_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.TpxError):
+        _lib.lib()
+    m = tpxl_b200.DiT(seq_length=8, in_channels=8, condition_channels=16, hidden_size=128, depth=1, num_heads=4, cond_drop_prob=0.1)
+    with pytest.raises(_lib.TpxError):
+        m.forward(torch.zeros(1, 8, 8), torch.zeros(1, dtype=torch.int64), torch.zeros(1, 3, 16))
+    with pytest.raises(_lib.TpxError):
+        list(tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v").ddim_sample_loop_progressive(
+            lambda *a, **k: None, (1, 8, 8), noise=torch.zeros(1, 8, 8), device="cpu"))
+
+
+def test_schedule_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sampler.npz"))
+    for k in (25, 50, 100, 200):
+        d = tpxl_b200.create_diffusion(f"ddim{k}", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+        assert np.array_equal(np.array(d.timestep_map), g[f"map_ddim{k}"])
+        np.testing.assert_allclose(d.alphas_cumprod, g[f"acp_ddim{k}"], rtol=1e-13)
+        assert d.num_timesteps == k
+    d = tpxl_b200.create_diffusion("", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    np.testing.assert_allclose(d.betas, g["betas_full"], rtol=1e-12)
+    assert np.array_equal(np.array(tpxl_b200.create_diffusion("10", "squaredcos_cap_v2", parameterization="v").timestep_map), g["map_sec10"])
+    d25 = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
+    for nm in ("posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_recipm1_alphas_cumprod"):
+        np.testing.assert_allclose(getattr(d25, nm), g[nm + "_ddim25"], rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="eps")
+    with pytest.raises(NotImplementedError):
+        tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="bogus")
+    with pytest.raises(ValueError):
+        tpxl_b200.create_diffusion("ddim600", "squaredcos_cap_v2", parameterization="v")
+
+
+def test_step_coefficients_are_fp32_rounded_like_extract_into_tensor():
+    import oracle
+    d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
+    s = oracle.diffusion.Schedule("ddim25")
+    for i in (0, 1, 12, 24):
+        for eta in (0.0, 0.5):
+            k = d.step_coefs(i, eta)
+            ab, abp = torch.tensor(s.alphas_cumprod[i]).float(), torch.tensor(s.alphas_cumprod_prev[i]).float()
+            sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+            assert k.sqrt_ab == float(torch.tensor(s.sqrt_alphas_cumprod[i]).float())
+            assert k.sigma == float(sigma)
+            # torch's CPU scalar sqrt is not always correctly rounded (1 ulp); numpy / CUDA sqrtf are
+            assert abs(k.c_x0 - float(torch.sqrt(abp))) <= 1.2e-7 * k.c_x0
+            assert k.c_eps == float(np.sqrt(np.float32(float(1 - abp - sigma ** 2))))
+            assert abs(k.c_eps - float(torch.sqrt(1 - abp - sigma ** 2))) <= 1.2e-7 * k.c_eps
+            assert k.nonzero == (0.0 if i == 0 else 1.0)
+
+
+def test_state_dict_contract_on_host(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    m = tpxl_b200.DiT(**{k: v for k, v in synth.FULL_DIT.items()})
+    assert {k: list(v) for k, v in m._shapes.items()} == keys["dit"]
+    tiny = dict(seq_length=8, in_channels=8, condition_channels=16, hidden_size=128, depth=1, num_heads=4, attn_proj_bias=True, cond_drop_prob=0.1)
+    m = tpxl_b200.DiT(**tiny)
+    sd = synth.synth_state_dict(synth.dit_shapes(**tiny), 5)
+    m.load_state_dict(sd)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    bad = dict(sd)
+    bad["blocks.0.attn.qkv.weight"] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict(bad)
+    del bad["blocks.0.attn.qkv.weight"]
+    with pytest.raises(RuntimeError, match="Missing key"):
+        m.load_state_dict(bad)
+    assert next(m.parameters()).device.type == "cpu"
+    v = tpxl_b200.VAE(**synth.FULL_VAE)
+    full_keys = {k: torch.zeros(s) for k, s in keys["vae"].items()}
+    res = v.load_state_dict(full_keys)          # encoder.* keys accepted, as in the released checkpoint
+    assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(NotImplementedError):
+        tpxl_b200.VAE(in_channels=6, latent_channels=4, out_channels=6, up_channels=[256, 32])
+    with pytest.raises(NotImplementedError):
+        v.encode(torch.zeros(1))
+
+
+def test_install_aliases_reference_module_paths():
+    tpxl_b200.install()
+    import importlib
+    assert importlib.import_module("models.dit_crossattn").DiT is tpxl_b200.DiT
+    assert importlib.import_module("models.vae3d_dib").VAE is tpxl_b200.VAE
+    from models.diffusion import create_diffusion
+    assert create_diffusion is tpxl_b200.create_diffusion
