@@ -1,0 +1,84 @@
+"""GPU: LayerNorm+modulate, CFG combine, sampler update, GroupNorm+SiLU against torch / the oracle."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+import tpxl_b200
+from tpxl_b200 import _lib
+from gpu_util import rel_l2, st
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("D", [128, 384, 1152])
+def test_ln_modulate(D):
+    rows, N = 700, 350
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    mod = (torch.randn(1, 3 * D, device="cuda") * 0.3).half()
+    out = torch.empty(rows, D, dtype=torch.float16, device="cuda")
+    _lib.check(_lib.lib().tpx_ln_modulate(x.data_ptr(), rows, D, 1e-6, mod.data_ptr(), mod[:, D:].data_ptr(), 3 * D, N, 1, out.data_ptr(), None, None, 0, st()))
+    ref = F.layer_norm(x, (D,), eps=1e-6) * (1 + mod[0, D:2 * D]).float() + mod[0, :D].float()
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max() < 1e-2 and rel_l2(out.float(), ref) < 5e-4
+
+
+def test_ln_modulate_with_null_branch_preadd():
+    D, N = 384, 64
+    x = torch.randn(2 * N, D, device="cuda")
+    x0 = x.clone()
+    mod = (torch.randn(1, 3 * D, device="cuda") * 0.3).half()
+    gate = (torch.randn(1, D, device="cuda")).half()
+    const = (torch.randn(D, device="cuda")).half()
+    out = torch.empty(2 * N, D, dtype=torch.float16, device="cuda")
+    _lib.check(_lib.lib().tpx_ln_modulate(x.data_ptr(), 2 * N, D, 1e-6, mod.data_ptr(), mod[:, D:].data_ptr(), 3 * D, N, 1, out.data_ptr(),
+                                          gate.data_ptr(), const.data_ptr(), N, st()))
+    xr = x0.clone()
+    xr[N:] += (gate[0].float() * const.float()).half().float()
+    ref = F.layer_norm(xr, (D,), eps=1e-6) * (1 + mod[0, D:2 * D]).float() + mod[0, :D].float()
+    torch.cuda.synchronize()
+    assert torch.equal(x[:N], x0[:N]) and (x[N:] - xr[N:]).abs().max() < 1e-6
+    assert rel_l2(out.float(), ref) < 5e-4
+
+
+def test_cfg_combine_matches_fp16_arithmetic():
+    both = torch.randn(2, 2048, 136, device="cuda").half()
+    out = torch.empty(1, 2048, 136, dtype=torch.float16, device="cuda")
+    _lib.check(_lib.lib().tpx_cfg_combine(both.data_ptr(), 2048 * 136, 6.0, out.data_ptr(), st()))
+    cond, uncond = both[0:1], both[1:2]
+    ref = uncond + 6.0 * (cond - uncond)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("ddim,eta", [(True, 0.0), (True, 0.5), (False, 0.0)])
+def test_sampler_step_matches_oracle(ddim, eta):
+    d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
+    s = oracle.diffusion.Schedule("ddim25")
+    x = torch.randn(2, 256, 68, device="cuda")
+    mo = torch.randn(2, 256, 136, device="cuda").half()
+    noise = torch.randn_like(x)
+    for i in (24, 7, 0):
+        got = d._step(ddim, x, mo, i, eta, False, noise)
+        ref = oracle.diffusion.ddim_step(s, x, mo.float(), i, eta, noise) if ddim else oracle.diffusion.ddpm_step(s, x, mo.float(), i, noise)
+        torch.cuda.synchronize()
+        tol = 2e-6 if ddim else 2e-3     # DDPM: the reference's fp16 (var+1)/2 arithmetic vs the oracle's fp32
+        assert (got["pred_xstart"] - ref["pred_xstart"]).abs().max() < 2e-6
+        assert (got["sample"] - ref["sample"]).abs().max() < tol * max(1.0, float(ref["sample"].abs().max()))
+
+
+@pytest.mark.parametrize("S3,Cc,silu", [(64, 256, 1), (512, 256, 1), (512, 32, 1), (64, 256, 0)])
+def test_groupnorm_silu(S3, Cc, silu):
+    P = 5
+    x = (torch.randn(P, S3, Cc, device="cuda") * 2 + 0.3).half()
+    gamma, beta = (torch.randn(Cc, device="cuda") * 0.1 + 1).half(), (torch.randn(Cc, device="cuda") * 0.1).half()
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().tpx_groupnorm_silu(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), P, S3, Cc, 32, 1e-5, silu, out.data_ptr(), st()))
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma.float(), beta.float(), eps=1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 1e-3

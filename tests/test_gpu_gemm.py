@@ -1,0 +1,69 @@
+"""GPU: the tcgen05/TMA GEMM and its fused epilogues through the C ABI, against fp32 torch math."""
+import pytest
+import torch
+
+from tpxl_b200 import _lib
+from gpu_util import dev, linear, linear_ref, rel_l2, st
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+@pytest.mark.parametrize("M,N,K,tile", [(128, 128, 64, 128), (256, 256, 128, 128), (512, 384, 256, 192), (512, 512, 1152, 256),
+                                        (300, 136, 1152, 128), (4096, 1152, 1152, 0), (1370, 2304, 768, 0), (4096, 1152, 4608, 0)])
+def test_linear_bias(M, N, K, tile):
+    A, W, b = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2), _rand(N, seed=3)
+    out = linear(A, W, b, tile_n=tile)
+    ref = linear_ref(A, W, b)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 2e-3, (M, N, K, tile)
+    assert (out.float() - ref.float()).abs().max() < 0.05
+
+
+def test_linear_identity_exact():
+    """A @ I^T must reproduce A bit-exactly: catches swizzle / descriptor / row-mapping errors with an exact check."""
+    M, K = 256, 128
+    A = _rand(M, K, seed=4)
+    W = torch.eye(K, device="cuda").half()
+    out = linear(A, W, None, tile_n=128)
+    torch.cuda.synchronize()
+    assert torch.equal(out, A)
+
+
+def test_linear_gelu_and_post_scale():
+    A, W, b = _rand(512, 256, seed=5), _rand(768, 256, scale=1 / 16, seed=6), _rand(768, seed=7)
+    assert rel_l2(linear(A, W, b, act=1), linear_ref(A, W, b, act=1)) < 2e-3
+    s = 72 ** -0.5
+    assert rel_l2(linear(A, W, b, post_scale=s), linear_ref(A, W, b, post_scale=s)) < 2e-3
+
+
+def test_linear_heads_layout_and_padding():
+    B, N, H, Dh, DhP, K = 2, 200, 16, 72, 80, 256
+    D = H * Dh
+    A, W, b = _rand(B * N, K, seed=8), _rand(3 * D, K, scale=1 / 16, seed=9), _rand(3 * D, seed=10)
+    outs = [torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
+    _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, 0, st()))
+    ref = linear_ref(A, W, b).reshape(B, N, 3, H, Dh)
+    torch.cuda.synchronize()
+    for w in range(3):
+        got = outs[w]
+        assert torch.all(got[..., Dh:] == 0), "zero padding of the head dim"
+        assert rel_l2(got[..., :Dh], ref[:, :, w].permute(0, 2, 1, 3)) < 2e-3
+
+
+def test_linear_gated_residual():
+    B, N, D, K = 2, 256, 384, 256
+    A, W, b = _rand(B * N, K, seed=11), _rand(D, K, scale=1 / 16, seed=12), _rand(D, seed=13)
+    gate = _rand(1, 5 * D, seed=14)          # one modulation row shared by both sequences (CFG: same t)
+    x = torch.randn(B * N, D, device="cuda")
+    x0 = x.clone()
+    _lib.check(_lib.lib().tpx_linear_gated(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), gate[:, 2 * D:].data_ptr(), 5 * D, 1, N, x.data_ptr(), D,
+                                           B * N, D, K, 0, st()))
+    ref = x0 + (gate[0, 2 * D:3 * D].float() * linear_ref(A, W, b).float()).half().float()
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max() < 2e-2 and rel_l2(x, ref) < 1e-3
