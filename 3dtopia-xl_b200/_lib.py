@@ -36,6 +36,9 @@ SIGNATURES = {
     "tpx_version": (_i, []),
     "tpx_last_error": (C.c_char_p, []),
     "tpx_device_check": (_i, []),
+    "tpx_launch_count": (_i64, []),
+    "tpx_profile_begin": (_i, []),
+    "tpx_profile_end": (_i, [C.POINTER(C.c_float), C.POINTER(_i64)]),
     "tpx_dit_create": (_i, [C.POINTER(DitConfig), C.POINTER(_vp)]),
     "tpx_dit_destroy": (None, [_vp]),
     "tpx_dit_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),

@@ -229,6 +229,7 @@ int launch_att(const __half* q, const __half* k, const __half* v, __half* out, i
         attr_set = true;
     }
     dim3 grid((Nq + ATT_BM - 1) / ATT_BM, H, B);
+    ProfScope prof(PROF_ATTENTION, st);
     kern<<<grid, ATT_THREADS, SMEM, st>>>(q, k, v, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f);
     TPX_LAUNCH_CHECK();
     return TPX_OK;

@@ -192,6 +192,16 @@ extern "C" {
 int tpx_version(void) { return TPX_VERSION; }
 const char* tpx_last_error(void) { return tpx::last_error(); }
 
+int64_t tpx_launch_count(void) { return tpx::launch_count(); }
+int tpx_profile_begin(void) { tpx::prof_begin(); return TPX_OK; }
+int tpx_profile_end(float* ms_by_class, int64_t* launches_by_class) {
+    TPX_CHECK(ms_by_class != nullptr && launches_by_class != nullptr, TPX_ERR_ARG, "profile_end: null argument");
+    long long n[PROF_NCLASS];
+    int rc = tpx::prof_end(ms_by_class, n);
+    for (int i = 0; i < PROF_NCLASS; ++i) launches_by_class[i] = n[i];
+    return rc;
+}
+
 int tpx_device_check(void) {
     int dev = 0;
     TPX_CUDA(cudaGetDevice(&dev));

@@ -82,6 +82,7 @@ int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift
                        int mod_batches, __half* out, const __half* pre_gate, const __half* pre_const, int pre_row0, cudaStream_t st) {
     TPX_CHECK(D % 128 == 0 && D <= 128 * LN_MAX_ITERS, TPX_ERR_SHAPE, "ln_modulate: hidden size %d must be a multiple of 128 and <= %d", D, 128 * LN_MAX_ITERS);
     if (rows <= 0) return TPX_OK;
+    ProfScope prof(PROF_LN, st);
     ln_modulate_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, D, eps, shift, scale, mod_bstride, rows_per_batch, mod_batches, out, pre_gate,
                                                        pre_const, pre_row0);
     TPX_LAUNCH_CHECK();
@@ -197,6 +198,7 @@ static int launch_gemv_t(const __half* W, const __half* bias, const void* in, co
                          int out_ld, cudaStream_t st) {
     TPX_CHECK(B >= 1 && B <= GEMV_MAXB, TPX_ERR_SHAPE, "gemv: batch %d must be in [1,%d]", B, GEMV_MAXB);
     TPX_CHECK(K % 8 == 0, TPX_ERR_SHAPE, "gemv: K %d must be a multiple of 8", K);
+    ProfScope prof(PROF_GEMV, st);
     const size_t smem = static_cast<size_t>(B) * ((K + 255) / 256) * 256 * sizeof(float);
     auto kern = gemv_kernel<IN, OUT>;
     if (smem > 48 * 1024) TPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(256) x_embed_kernel(const float* __restrict__ 
 
 int launch_x_embed(const float* x, const __half* W, const __half* bias, int rows, int Cin, int D, float* out, long long dup_offset, cudaStream_t st) {
     if (rows <= 0) return TPX_OK;
+    ProfScope prof(PROF_GEMV, st);
     x_embed_kernel<<<(rows + XE_ROWS - 1) / XE_ROWS, 256, XE_ROWS * Cin * sizeof(float), st>>>(x, W, bias, rows, Cin, D, out, dup_offset);
     TPX_LAUNCH_CHECK();
     return TPX_OK;
@@ -280,6 +283,7 @@ __global__ void cfg_combine_kernel(const __half* __restrict__ both, long long n_
 int launch_cfg_combine(const __half* both, long long n_half, float s, __half* out, cudaStream_t st) {
     TPX_CHECK(n_half % 8 == 0, TPX_ERR_SHAPE, "cfg_combine: element count %lld must be a multiple of 8", n_half);
     const long long thr = n_half / 8;
+    ProfScope prof(PROF_ELEMWISE, st);
     cfg_combine_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, st>>>(both, n_half, s, out);
     TPX_LAUNCH_CHECK();
     return TPX_OK;
@@ -347,6 +351,7 @@ int launch_sampler_step(int ddim, const float* x, const void* mo, int mo_is_half
                         float* x_prev, float* x0_out, cudaStream_t st) {
     if (n <= 0) return TPX_OK;
     const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    ProfScope prof(PROF_ELEMWISE, st);
     if (ddim) {
         if (mo_is_half) ddim_step_kernel<__half><<<grid, 256, 0, st>>>(x, static_cast<const __half*>(mo), noise, n, C, k, x_prev, x0_out);
         else ddim_step_kernel<float><<<grid, 256, 0, st>>>(x, static_cast<const float*>(mo), noise, n, C, k, x_prev, x0_out);

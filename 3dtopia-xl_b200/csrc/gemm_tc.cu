@@ -1,12 +1,14 @@
 // Host launcher for the tcgen05 GEMM: tensor-map construction (cached), tile-shape dispatch.
 #include "gemm_tc.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 namespace tpx {
 
@@ -22,6 +24,50 @@ const char* last_error() { return g_err; }
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
     return TPX_ERR_CUDA;
+}
+
+// ---- launch counter + optional event profiling ------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(int cls, cudaStream_t s) : idx(-1), st(s) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    idx = static_cast<int>(g_prof_recs.size());
+    g_prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof_recs[idx].b, st);
+}
+void prof_begin() {
+    for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+    g_prof_on = true;
+}
+int prof_end(float* ms_by_class, long long* n_by_class) {
+    g_prof_on = false;
+    TPX_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < PROF_NCLASS; ++i) { ms_by_class[i] = 0.f; n_by_class[i] = 0; }
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_by_class[r.cls] += ms; n_by_class[r.cls] += 1; }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    return TPX_OK;
 }
 
 int gemm_num_sms() {
@@ -123,6 +169,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     TPX_CHECK(p.M > 0 && p.N > 0 && p.K > 0, TPX_ERR_SHAPE, "gemm: empty problem %d x %d x %d", p.M, p.N, p.K);
     TPX_CHECK(p.N % 8 == 0 && p.K % 8 == 0, TPX_ERR_SHAPE, "gemm: N (%d) and K (%d) must be multiples of 8", p.N, p.K);
     const int bk = (p.a_mode == AMODE_CONV3 && p.conv_C == 32) ? 32 : 64;
+    ProfScope prof(p.a_mode == AMODE_CONV3 ? PROF_CONV_GEMM : PROF_GEMM, stream);
     GemmArgs a = p.args;
     a.M = p.M;
     a.N = p.N;

@@ -12,6 +12,9 @@ struct SamplerCoefs {
 };
 
 const char* last_error();
+long long launch_count();
+void prof_begin();
+int prof_end(float* ms_by_class, long long* n_by_class);
 
 // elementwise.cu
 int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift, const __half* scale, int mod_bstride, int rows_per_batch,

@@ -26,7 +26,22 @@ int cuda_fail(cudaError_t e, const char* what);
     do {                                                                 \
         if (!(cond)) { ::tpx::set_error(__VA_ARGS__); return (code); }   \
     } while (0)
-#define TPX_LAUNCH_CHECK() TPX_CUDA(cudaGetLastError())
+void note_launch();
+#define TPX_LAUNCH_CHECK()              \
+    do {                                \
+        ::tpx::note_launch();           \
+        TPX_CUDA(cudaGetLastError());   \
+    } while (0)
+
+// Optional per-kernel-class device timing (bench.py roofline leg): RAII scope that brackets the launches
+// issued inside it with a CUDA event pair on the launching stream when profiling is enabled.
+enum ProfClass : int { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LN = 2, PROF_GEMV = 3, PROF_ELEMWISE = 4, PROF_CONV_GEMM = 5, PROF_GROUPNORM = 6, PROF_VAE_MISC = 7, PROF_NCLASS = 8 };
+struct ProfScope {
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+    int idx;
+    cudaStream_t st;
+};
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

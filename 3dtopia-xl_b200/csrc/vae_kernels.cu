@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) vae_conv_in_kernel(const ZT* __restrict__
 int launch_vae_conv_in(const void* z, int z_dtype, const __half* w_pq, const __half* b_pq, const __half* W, const __half* bias, int P, int C,
                        __half* out, cudaStream_t st) {
     if (P <= 0) return TPX_OK;
+    ProfScope prof(PROF_VAE_MISC, st);
     if (z_dtype == TPX_DTYPE_F32) vae_conv_in_kernel<float><<<P, 256, 0, st>>>(static_cast<const float*>(z), w_pq, b_pq, W, bias, C, out);
     else if (z_dtype == TPX_DTYPE_F16) vae_conv_in_kernel<__half><<<P, 256, 0, st>>>(static_cast<const __half*>(z), w_pq, b_pq, W, bias, C, out);
     else { set_error("vae_conv_in: unsupported latent dtype %d", z_dtype); return TPX_ERR_ARG; }
@@ -58,11 +59,10 @@ __global__ void __launch_bounds__(256) groupnorm_silu_kernel(const __half* __res
                                                              const __half* __restrict__ beta, int S3, int C, int groups, float eps, int apply_silu,
                                                              __half* __restrict__ out) {
     __shared__ float s_sum[GN_MAXC], s_sq[GN_MAXC], s_scale[GN_MAXC], s_shift[GN_MAXC];
+    __shared__ float s_part[256 * 16];
     const int p = blockIdx.x;
     const int oct = C >> 3;                    // 16-byte octets per voxel
     const int total = S3 * oct;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-    __syncthreads();
     const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<size_t>(p) * S3 * C);
     // blockDim (256) is a multiple of oct (<= 32), so a thread always sees the same octet
     const int my_oct = threadIdx.x % oct;
@@ -79,10 +79,23 @@ __global__ void __launch_bounds__(256) groupnorm_silu_kernel(const __half* __res
             lq[k] = fmaf(f, f, lq[k]);
         }
     }
+    // deterministic cross-thread reduction (fixed order; run-to-run bit-identical): per-thread partials -> smem,
+    // then channel c sums the partials of the 256/oct threads that own its octet.
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_sum[my_oct * 8 + k], ls[k]);
-        atomicAdd(&s_sq[my_oct * 8 + k], lq[k]);
+        s_part[threadIdx.x * 16 + k] = ls[k];
+        s_part[threadIdx.x * 16 + 8 + k] = lq[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int o = c >> 3, k = c & 7;
+        float a = 0.f, b = 0.f;
+        for (int t = o; t < 256; t += oct) {
+            a += s_part[t * 16 + k];
+            b += s_part[t * 16 + 8 + k];
+        }
+        s_sum[c] = a;
+        s_sq[c] = b;
     }
     __syncthreads();
     const int cpg = C / groups;
@@ -121,6 +134,7 @@ int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* be
     TPX_CHECK(C % 8 == 0 && C <= GN_MAXC && 256 % (C / 8) == 0 && groups > 0 && C % groups == 0, TPX_ERR_SHAPE,
               "groupnorm: channels %d / groups %d unsupported (C%%8==0, C<=%d, C/8 | 256)", C, groups, GN_MAXC);
     if (P <= 0) return TPX_OK;
+    ProfScope prof(PROF_GROUPNORM, st);
     groupnorm_silu_kernel<<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
     TPX_LAUNCH_CHECK();
     return TPX_OK;

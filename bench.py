@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — DiT denoising steps/sec (2048 primitive tokens, CFG x2) on N B200s, plus VAE decode ms.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): image-conditioned DDIM, CFG 6, 2048 tokens x 1370 context tokens, fp16, ONE
+sample per GPU.  A *step* is one `forward_with_cfg` (two sequences) + the sampler update.  Synthetic weights of the
+shipped architecture and synthetic inputs of the shipped shapes (no checkpoints or images exist offline).
+
+  value    steps/s, whole job: inputs already in HBM, device-timed (CUDA events on the launch stream), max over ranks.
+  e2e      the same through the public API from HOST buffers: every step copies x_t from pinned host memory, runs
+           forward_with_cfg + the update, and reads x_{t-1} back to pinned host memory; the per-image conditioning
+           upload and K/V hoist are inside the timed region too.
+  roofline tcgen05 GEMM kernel family: algorithmic FLOPs of the GEMMs in a step / their summed device time, measured
+           live with per-launch CUDA events (a separate profiled pass of the same steps); peak from MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the oracle port of the reference path (oracle/dit.py, fp32) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DiT steps/sec (2048 prim tokens, CFG x2)"
+UNIT = "steps/s"
+N_TOK, M_CTX, D, H, L, DC, CIN = 2048, 1370, 1152, 16, 28, 768, 68
+CFG_SCALE = 6.0
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+# ---- algorithmic work (SURVEY.md §8d term table; FLOPs = 2*MACs, per sequence of 2048 tokens) ----------------------
+def flops_terms():
+    g = lambda m, n, k: 2.0 * m * n * k
+    per_block = dict(
+        adaln=g(1, 9 * D, D), ca_q=g(N_TOK, D, D), ca_k=g(M_CTX, D, DC), ca_v=g(M_CTX, D, DC), ca_qk=g(N_TOK, M_CTX, D), ca_pv=g(N_TOK, M_CTX, D),
+        ca_proj=g(N_TOK, D, D), sa_qkv=g(N_TOK, 3 * D, D), sa_qk=g(N_TOK, N_TOK, D), sa_pv=g(N_TOK, N_TOK, D), sa_proj=g(N_TOK, D, D),
+        fc1=g(N_TOK, 4 * D, D), fc2=g(N_TOK, D, 4 * D))
+    embed_final = g(N_TOK, D, CIN) + g(1, D, 256) + g(1, D, D) + g(1, 2 * D, D) + g(N_TOK, 2 * CIN, D)
+    return per_block, embed_final
+
+
+def f_step_algorithmic() -> float:
+    pb, ef = flops_terms()
+    return 2 * (L * sum(pb.values()) + ef)            # 6.343e12
+
+
+def f_step_executed() -> dict:
+    """What the build actually executes per step: cross K/V hoisted out of the step, the null half skips cross-attention."""
+    pb, ef = flops_terms()
+    gemm_cond = pb["ca_q"] + pb["ca_proj"]
+    gemm_both = pb["sa_qkv"] + pb["sa_proj"] + pb["fc1"] + pb["fc2"]
+    gemm = L * (gemm_cond + 2 * gemm_both) + 2 * 2.0 * N_TOK * 2 * CIN * D
+    attn = L * (pb["ca_qk"] + pb["ca_pv"] + 2 * (pb["sa_qk"] + pb["sa_pv"]))
+    return {"gemm": gemm, "attention": attn, "total": gemm + attn}
+
+
+F_VAE = 4.593e12   # 2242.8 MFLOP per primitive x 2048
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {k: float(d[k]) for k in FALLBACK_PEAKS if k in d} | {"source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS, source="fallback (B200_PROFILING.md)")
+
+
+# ---- clocks sampler -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, start_idx=0):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r.split(", ") for r in self.rows[start_idx:] if r.count(",") >= 6] or [r.split(", ") for r in self.rows if r.count(",") >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[0]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].strip().lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+# ---- reference arm / cpu baseline: the oracle port on the host cores -------------------------------------------------
+def cpu_oracle_steps_per_s(sample_blocks: int, reps: int):
+    """Times forward_with_cfg of the ORACLE (oracle/dit.py, fp32, the reference's CPU arithmetic) at full width on a
+    `sample_blocks`-deep stack and extrapolates linearly in depth to 28 blocks (blocks are identical in cost)."""
+    import torch
+    import oracle
+    from tpxl_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = dict(synth.FULL_DIT, depth=sample_blocks)
+    g = torch.Generator().manual_seed(0)
+    sd = {k: torch.randn(s, generator=g) * 0.02 for k, s in synth.dit_shapes(**cfg).items()}
+    x, y = torch.randn(1, N_TOK, CIN, generator=g), torch.randn(1, M_CTX, DC, generator=g)
+    t = torch.tensor([960])
+    times = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            oracle.dit.forward_with_cfg(sd, x, t, y, CFG_SCALE, H, "fp32")
+            times.append(time.perf_counter() - t0)
+    t_sample = min(times)
+    t_step = t_sample * (L / sample_blocks)
+    return 1.0 / t_step, t_sample, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    blocks = 2
+    per = []
+    for i in range(args.warmup + args.steps):
+        sps, t_sample, cores = cpu_oracle_steps_per_s(blocks, 1)
+        if i >= args.warmup:
+            per.append(sps)
+    val = statistics.median(per)
+    sample = f"forward_with_cfg (B=1: 2 sequences x 2048 tokens x 1370 ctx, fp32) on a {blocks}-block stack per step, extrapolated x{L}/{blocks} in depth"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "configs[1]: DDIM step, CFG 6, 2048 tokens x 1370 ctx, B=1 (CPU: oracle port of the reference path)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import tpxl_b200
+    from tpxl_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    lib = _lib.lib()
+    K, W = args.steps, max(args.warmup, 3)
+
+    # model (random init of the shipped architecture), one sample per GPU, noise/conditioning drawn like inference.py:313-317
+    sd = synth.device_state_dict(synth.dit_shapes(**synth.FULL_DIT), 1234, dev, torch.float16)
+    model = tpxl_b200.DiT(**synth.FULL_DIT)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    del sd
+    g = torch.Generator().manual_seed(42 + rank)
+    _ = torch.randn(1, N_TOK, 1, 4, 4, 4, generator=g)
+    x_host = torch.randn(1, N_TOK, CIN, generator=g).pin_memory()
+    y_host = torch.randn(1, M_CTX, DC, generator=torch.Generator().manual_seed(43 + rank)).pin_memory()
+    respacing = "ddim25"
+    diffusion = tpxl_b200.create_diffusion(respacing, noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    diffusion.match_reference_rng = True
+    nT = diffusion.num_timesteps
+    t_all = torch.tensor(diffusion.timestep_map, dtype=torch.int64, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(x, y, i):
+        t = t_all[i % nT].expand(1).contiguous()
+        out = model.forward_with_cfg(x, t, y, cfg_scale=CFG_SCALE, precision_dtype=torch.float16, enable_amp=True)
+        noise = torch.randn_like(x)
+        return diffusion._step(True, x, out, i % nT, 0.0, False, noise)["sample"]
+
+    # ---- device-resident timing ("value") ----
+    x = x_host.to(dev)
+    y = y_host.to(dev)
+    with torch.no_grad():
+        for i in range(W):
+            x = one_step(x, y, nT - 1 - i)
+        barrier()
+        clocks = ClockSampler(local) if rank == 0 else None
+        mark = clocks.mark() if clocks else 0
+        l0 = lib.tpx_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            x = one_step(x, y, nT - 1 - (i % nT))
+        e1.record()
+        barrier()
+        launches = lib.tpx_launch_count() - l0
+        ms_dev = e0.elapsed_time(e1)
+        clock_info = clocks.stop(mark) if clocks else None
+
+        # ---- end to end from host buffers ("e2e") ----
+        x_pin_out = torch.empty_like(x_host).pin_memory()
+        xd = torch.empty(1, N_TOK, CIN, device=dev)
+        for i in range(2):
+            xd.copy_(x_host, non_blocking=True)
+            x_pin_out.copy_(one_step(xd, y, nT - 1 - i), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        y_e2e = y_host.to(dev, non_blocking=True)          # per-image conditioning upload + K/V hoist inside the timed region
+        cur = x_host
+        for i in range(K):
+            xd.copy_(cur, non_blocking=True)
+            x_pin_out.copy_(one_step(xd, y_e2e, nT - 1 - (i % nT)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the host consumes the step result (progressive preview, inference.py:325)
+            cur = x_pin_out
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+        h2d = x_host.numel() * 4 + 8 + (y_host.numel() * 4) / K
+        d2h = x_host.numel() * 4
+
+        # ---- per-kernel-class device time (roofline leg): same steps, every launch bracketed by events ----
+        nprof = min(K, 5)
+        ms_cls, n_cls = (C.c_float * 8)(), (C.c_int64 * 8)()
+        _lib.check(lib.tpx_profile_begin())
+        for i in range(nprof):
+            x = one_step(x, y, nT - 1 - i)
+        _lib.check(lib.tpx_profile_end(ms_cls, n_cls))
+        ms_cls = [v / nprof for v in ms_cls]
+        n_cls = [int(v) // nprof for v in n_cls]
+
+        # ---- VAE decode of 2048 primitives (config #4), fp16 in/out ----
+        vae_ms = None
+        if rank == 0 and not args.no_vae:
+            vsd = synth.device_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 1236, dev, torch.float16)
+            vae = tpxl_b200.VAE(**synth.FULL_VAE)
+            vae.load_state_dict(vsd)
+            vae = vae.to(dev)
+            z = (torch.randn(2048, 64, generator=torch.Generator().manual_seed(44)) * torch.tensor(synth.LATENT_STD[4:]) + torch.tensor(synth.LATENT_MEAN[4:])).reshape(2048, 1, 4, 4, 4).to(dev).half()
+            for _ in range(3):
+                vae.decode(z)
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(5):
+                vae.decode(z)
+            v1.record()
+            torch.cuda.synchronize()
+            vae_ms = v0.elapsed_time(v1) / 5
+            _lib.check(lib.tpx_profile_begin())
+            vae.decode(z)
+            vms, vn = (C.c_float * 8)(), (C.c_int64 * 8)()
+            _lib.check(lib.tpx_profile_end(vms, vn))
+            vae_cls = {"conv_gemm_ms": vms[5], "gemm_ms": vms[0], "groupnorm_ms": vms[6], "attention_ms": vms[1], "other_ms": vms[7]}
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+        dist.gather(x, gathered, dst=0)                     # final latents to rank 0 over NCCL/NVLink (0.56 MB per sample)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    peak_tf = peaks["bf16_tflops_sustained"]               # kernels timed inside a long step -> sustained figure
+    steps_per_s = world * K / (ms_dev / 1e3)
+    fx = f_step_executed()
+    gemm_ms = ms_cls[0]
+    gemm_tf = fx["gemm"] / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    attn_tf = fx["attention"] / (ms_cls[1] / 1e3) / 1e12 if ms_cls[1] > 0 else 0.0
+    step_ms_prof = sum(ms_cls)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": "configs[1]: image-cond DDIM-25 step, CFG 6, 2048 tokens x 1370 ctx tokens, fp16, 1 sample per GPU (2 sequences per forward)",
+                   "samples_per_gpu": 1, "respacing": respacing, "cfg_scale": CFG_SCALE, "parallelism": f"dp{world} (one sample per GPU, no collective in the step loop)",
+                   "l2": "each step streams 1.8 GB of fp16 weights (> 126 MB L2), so no separate L2 flush is needed"},
+        "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA GEMM family, all DiT linears)", "achieved": gemm_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                     "flops_per_step": fx["gemm"], "launches_per_step": n_cls[0], "ms_per_step": gemm_ms,
+                     "share_of_step": gemm_ms / step_ms_prof if step_ms_prof else None},
+        "attention": {"kernel": "attention_kernel<80> (mma.sync flash attention)", "achieved": attn_tf, "unit": "TFLOP/s", "frac": attn_tf / peak_tf if peak_tf else None,
+                      "ms_per_step": ms_cls[1], "launches_per_step": n_cls[1], "share_of_step": ms_cls[1] / step_ms_prof if step_ms_prof else None},
+        "step_breakdown_ms": {"gemm": ms_cls[0], "attention": ms_cls[1], "ln_modulate": ms_cls[2], "gemv_embed": ms_cls[3], "cfg_sampler": ms_cls[4]},
+        "step_utilisation": {"F_step_algorithmic": f_step_algorithmic(), "F_step_executed": fx["total"],
+                             "frac_of_peak_algorithmic": steps_per_s / world * f_step_algorithmic() / 1e12 / peak_tf,
+                             "frac_of_peak_executed": steps_per_s / world * fx["total"] / 1e12 / peak_tf},
+    }
+    if vae_ms is not None:
+        line["vae_decode"] = {"ms": vae_ms, "primitives": 2048, "dtype": "fp16", "achieved_tflops": F_VAE / (vae_ms / 1e3) / 1e12,
+                              "frac": F_VAE / (vae_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "peak": peaks["bf16_tflops"], "breakdown_ms": vae_cls}
+    if not args.no_cpu and world >= 1:
+        try:
+            sps, t_sample, cores = cpu_oracle_steps_per_s(2, 3)
+            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"oracle forward_with_cfg fp32, 2-block stack at full width, best of 3 ({t_sample:.2f} s), extrapolated x14 to 28 blocks"}
+        except Exception as ex:  # never lose the GPU line over the CPU leg
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

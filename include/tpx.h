@@ -32,6 +32,14 @@ int tpx_version(void);
 const char* tpx_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), else TPX_ERR_CUDA. */
 int tpx_device_check(void);
+/* Measurement hooks (bench.py): total kernels launched by this library so far; and an optional mode that brackets
+ * every launch with a CUDA event pair on its stream.  profile_end synchronises the device and returns, per kernel
+ * class, the summed device time (ms) and launch count.  Classes: 0 tcgen05 GEMM, 1 attention, 2 LayerNorm+modulate,
+ * 3 GEMV/embedders, 4 CFG/sampler, 5 implicit-GEMM conv, 6 GroupNorm, 7 other VAE. */
+#define TPX_PROF_NCLASS 8
+int64_t tpx_launch_count(void);
+int tpx_profile_begin(void);
+int tpx_profile_end(float* ms_by_class, int64_t* launches_by_class);
 
 /* ------------------------------------------------------------------------------------------------------------
  * DiT  — models/dit_crossattn.py:111-213 (class DiT), constructor kwargs as in configs/inference_dit.yml:52-62

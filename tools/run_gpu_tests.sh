@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 rc_all=0
 for f in tests/test_gpu_gemm.py tests/test_gpu_elementwise.py tests/test_gpu_attention.py tests/test_gpu_dit.py tests/test_gpu_sampler.py tests/test_gpu_vae.py; do
   n=$(basename $f .py)
-  timeout $T python -m pytest $f -q -m gpu -x --no-header -p no:cacheprovider -s > gpurun_out/$n.log 2>&1
+  timeout $T python -m pytest $f -q -m gpu --timeout 300 --no-header -p no:cacheprovider -s > gpurun_out/$n.log 2>&1
   rc=$?
   echo "$n rc=$rc : $(tail -n 1 gpurun_out/$n.log)"
   [ $rc -ne 0 ] && rc_all=1
