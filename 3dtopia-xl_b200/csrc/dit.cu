@@ -203,11 +203,15 @@ int tpx_profile_end(float* ms_by_class, int64_t* launches_by_class) {
 }
 
 int tpx_device_check(void) {
+    static int checked[64] = {0};   // per device ordinal: 0 unknown, 1 ok (attribute queries are cheap, but this sits on per-kernel entry points)
     int dev = 0;
     TPX_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    TPX_CUDA(cudaGetDeviceProperties(&prop, dev));
-    TPX_CHECK(prop.major == 10, TPX_ERR_CUDA, "libtpx_b200 is sm_100a only; device %d is sm_%d%d (no fallback path exists)", dev, prop.major, prop.minor);
+    if (dev >= 0 && dev < 64 && checked[dev] == 1) return TPX_OK;
+    int major = 0, minor = 0;
+    TPX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    TPX_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    TPX_CHECK(major == 10, TPX_ERR_CUDA, "libtpx_b200 is sm_100a only; device %d is sm_%d%d (no fallback path exists)", dev, major, minor);
+    if (dev >= 0 && dev < 64) checked[dev] = 1;
     return TPX_OK;
 }
 

@@ -56,7 +56,7 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias + gate tile, fp32*/;
     static_assert(B_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "stage operands must stay 1024-B aligned");
     static_assert(BN % 16 == 0 && BN <= 256, "UMMA N");
 };
@@ -77,88 +77,152 @@ union Pack8 {
     __half h[8];
 };
 
-// ---- epilogue for one 8-column group of one row ---------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epi_group8(const GemmArgs& g, int row, int col, const uint32_t* acc /*8 fp32 bit patterns*/) {
-    float v[8];
+// ---- epilogue ---------------------------------------------------------------------------------------------------
+// One thread owns one accumulator row; columns arrive in chunks of CH (32) fp32 values from TMEM.  bias (and the
+// adaLN gate when it is uniform over the tile's rows) are staged once per tile in shared memory as fp32, every
+// global load of a chunk is issued before the first use, and the (which, head, d) split of a column is advanced
+// incrementally instead of divided out per group.
+struct HeadCursor {
+    int which, head, d;
+};
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    // 0.5 x (1 + tanh(u)),  tanh(u) = 1 - 2 / (1 + e^{2u});  MUFU.EX2 + MUFU.RCP, abs error ~1e-7 (fp16 output)
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float e = __expf(2.0f * u);
+    const float th = 1.0f - __fdividef(2.0f, 1.0f + e);
+    return 0.5f * x * (1.0f + th);
+}
+
+template <int EPI, int CH>
+__device__ __forceinline__ void epi_chunk(const GemmArgs& g, const float* __restrict__ sb, const float* __restrict__ sg, bool gate_in_smem, int row,
+                                          bool row_ok, int col0, int c0, const uint32_t* acc, HeadCursor& hc, size_t head_row_off) {
+    constexpr int NG = CH / 8;
+    float v[CH];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]);
-    if (g.bias != nullptr) {
-        Pack8 b;
-        b.u = *reinterpret_cast<const uint4*>(g.bias + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += __half2float(b.h[i]);
+    for (int i = 0; i < CH; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+        v[i] = __uint_as_float(acc[i]) + b4.x;
+        v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
+        v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
+        v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
     }
+    bool ok[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) ok[j] = row_ok && (col0 + j * 8 < g.N);
+
     if constexpr (EPI == EPI_STORE || EPI == EPI_GELU) {
-        Pack8 o;
+        __half* op = g.out0 + static_cast<size_t>(row) * g.ldo + col0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float x = h2f_round(v[i]);
-            if constexpr (EPI == EPI_GELU) x = gelu_tanh(x);
-            else if (g.post_scale != 1.0f) x = x * g.post_scale;
-            o.h[i] = __float2half_rn(x);
+        for (int j = 0; j < NG; ++j) {
+            Pack8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x = h2f_round(v[j * 8 + i]);
+                if constexpr (EPI == EPI_GELU) x = gelu_tanh_fast(x);
+                else if (g.post_scale != 1.0f) x = x * g.post_scale;
+                o.h[i] = __float2half_rn(x);
+            }
+            if (ok[j]) *reinterpret_cast<uint4*>(op + j * 8) = o.u;
         }
-        *reinterpret_cast<uint4*>(g.out0 + static_cast<size_t>(row) * g.ldo + col) = o.u;
     } else if constexpr (EPI == EPI_HEADS) {
-        const int which = col / g.split_cols;
-        const int c = col - which * g.split_cols;
-        const int head = c / g.Dh;
-        const int d = c - head * g.Dh;
-        const int b = row / g.Nseq;
-        const int n = row - b * g.Nseq;
-        __half* base = which == 0 ? g.out0 : (which == 1 ? g.out1 : g.out2);
-        __half* dst = base + (static_cast<size_t>(b * g.H + head) * g.Nseq + n) * g.DhP + d;
-        Pack8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float x = h2f_round(v[i]);
-            if (g.post_scale != 1.0f && which == 0) x = x * g.post_scale;
-            o.h[i] = __float2half_rn(x);
-        }
-        *reinterpret_cast<uint4*>(dst) = o.u;
-        if (d + 8 == g.Dh) {  // last real group of this head: write the zero padding d in [Dh, DhP)
-            for (int p = g.Dh; p < g.DhP; p += 8) *reinterpret_cast<uint4*>(dst + (p - d)) = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < NG; ++j) {
+            __half* base = hc.which == 0 ? g.out0 : (hc.which == 1 ? g.out1 : g.out2);
+            __half* dst = base + head_row_off + static_cast<size_t>(hc.head) * g.Nseq * g.DhP + hc.d;
+            Pack8 o;
+            const bool sc = g.post_scale != 1.0f && hc.which == 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x = h2f_round(v[j * 8 + i]);
+                if (sc) x = x * g.post_scale;
+                o.h[i] = __float2half_rn(x);
+            }
+            if (ok[j]) {
+                *reinterpret_cast<uint4*>(dst) = o.u;
+                if (hc.d + 8 == g.Dh)   // last real group of this head: write the zero padding d in [Dh, DhP)
+                    for (int p = g.Dh; p < g.DhP; p += 8) *reinterpret_cast<uint4*>(dst + (p - hc.d)) = make_uint4(0, 0, 0, 0);
+            }
+            hc.d += 8;
+            if (hc.d >= g.Dh) {
+                hc.d = 0;
+                if (++hc.head == g.H) { hc.head = 0; ++hc.which; }
+            }
         }
     } else if constexpr (EPI == EPI_GATED) {
-        const int b = (row / g.rows_per_batch) % g.gate_batches;
-        Pack8 gt;
-        gt.u = *reinterpret_cast<const uint4*>(g.gate + static_cast<size_t>(b) * g.gate_bstride + col);
-        float* xp = g.xres + static_cast<size_t>(row) * g.ldx + col;
-        float4 x0 = *reinterpret_cast<float4*>(xp);
-        float4 x1 = *reinterpret_cast<float4*>(xp + 4);
-        float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float* xp = g.xres + static_cast<size_t>(row) * g.ldx + col0;
+        float4 xr[2 * NG];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xs[i] += h2f_round(__half2float(gt.h[i]) * h2f_round(v[i]));
-        *reinterpret_cast<float4*>(xp) = make_float4(xs[0], xs[1], xs[2], xs[3]);
-        *reinterpret_cast<float4*>(xp + 4) = make_float4(xs[4], xs[5], xs[6], xs[7]);
-    } else if constexpr (EPI == EPI_RESID_SCALE) {
-        const size_t off = static_cast<size_t>(row) * g.ldo + col;
-        Pack8 o;
-        if (g.resid != nullptr) {
-            Pack8 r;
-            r.u = *reinterpret_cast<const uint4*>(g.resid + off);
+        for (int j = 0; j < NG; ++j) {
+            xr[2 * j] = ok[j] ? *reinterpret_cast<const float4*>(xp + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xr[2 * j + 1] = ok[j] ? *reinterpret_cast<const float4*>(xp + j * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float gt[CH];
+        if (gate_in_smem) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += __half2float(r.h[i]);
+            for (int i = 0; i < CH; i += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + i);
+                gt[i] = g4.x; gt[i + 1] = g4.y; gt[i + 2] = g4.z; gt[i + 3] = g4.w;
+            }
+        } else {
+            const int b = (row / g.rows_per_batch) % g.gate_batches;
+            const __half* gp = g.gate + static_cast<size_t>(b) * g.gate_bstride + col0;
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                Pack8 t;
+                t.u = ok[j] ? *reinterpret_cast<const uint4*>(gp + j * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gt[j * 8 + i] = __half2float(t.h[i]);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.h[i] = __float2half_rn(v[i] * g.alpha);
-        *reinterpret_cast<uint4*>(g.out0 + off) = o.u;
+        for (int j = 0; j < NG; ++j) {
+            float4 a = xr[2 * j], c = xr[2 * j + 1];
+            a.x += h2f_round(gt[j * 8 + 0] * h2f_round(v[j * 8 + 0]));
+            a.y += h2f_round(gt[j * 8 + 1] * h2f_round(v[j * 8 + 1]));
+            a.z += h2f_round(gt[j * 8 + 2] * h2f_round(v[j * 8 + 2]));
+            a.w += h2f_round(gt[j * 8 + 3] * h2f_round(v[j * 8 + 3]));
+            c.x += h2f_round(gt[j * 8 + 4] * h2f_round(v[j * 8 + 4]));
+            c.y += h2f_round(gt[j * 8 + 5] * h2f_round(v[j * 8 + 5]));
+            c.z += h2f_round(gt[j * 8 + 6] * h2f_round(v[j * 8 + 6]));
+            c.w += h2f_round(gt[j * 8 + 7] * h2f_round(v[j * 8 + 7]));
+            if (ok[j]) {
+                *reinterpret_cast<float4*>(xp + j * 8) = a;
+                *reinterpret_cast<float4*>(xp + j * 8 + 4) = c;
+            }
+        }
+    } else if constexpr (EPI == EPI_RESID_SCALE) {
+        const size_t off = static_cast<size_t>(row) * g.ldo + col0;
+        Pack8 rs[NG];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) rs[j].u = (ok[j] && g.resid != nullptr) ? *reinterpret_cast<const uint4*>(g.resid + off + j * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            Pack8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.h[i] = __float2half_rn((v[j * 8 + i] + __half2float(rs[j].h[i])) * g.alpha);
+            if (ok[j]) *reinterpret_cast<uint4*>(g.out0 + off + j * 8) = o.u;
+        }
     } else if constexpr (EPI == EPI_CONVT2) {
-        const int abc = col / g.split_cols;
-        const int co = col - abc * g.split_cols;
         const int p = row >> 6, vox = row & 63;
         const int z = vox >> 4, y = (vox >> 2) & 3, x = vox & 3;
-        const int oz = 2 * z + (abc >> 2), oy = 2 * y + ((abc >> 1) & 1), ox = 2 * x + (abc & 1);
-        Pack8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.h[i] = __float2half_rn(v[i]);
-        *reinterpret_cast<uint4*>(g.out0 + (static_cast<size_t>(p) * 512 + (oz * 8 + oy) * 8 + ox) * g.split_cols + co) = o.u;
+        for (int j = 0; j < NG; ++j) {
+            const int col = col0 + j * 8;
+            const int abc = col / g.split_cols;
+            const int co = col - abc * g.split_cols;
+            const int oz = 2 * z + (abc >> 2), oy = 2 * y + ((abc >> 1) & 1), ox = 2 * x + (abc & 1);
+            Pack8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.h[i] = __float2half_rn(v[j * 8 + i]);
+            if (ok[j]) *reinterpret_cast<uint4*>(g.out0 + (static_cast<size_t>(p) * 512 + (oz * 8 + oy) * 8 + ox) * g.split_cols + co) = o.u;
+        }
     } else if constexpr (EPI == EPI_NCDHW) {
         const int p = row / g.S3, vox = row - p * g.S3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int co = col + i;
-            if (co < g.n_valid) {
+        for (int i = 0; i < CH; ++i) {
+            const int co = col0 + i;
+            if (row_ok && co < g.n_valid) {
                 const size_t off = (static_cast<size_t>(p) * g.n_valid + co) * g.S3 + vox;
                 if (g.out32 != nullptr) g.out32[off] = v[i];
                 else g.out0[off] = __float2half_rn(v[i]);
@@ -166,6 +230,8 @@ __device__ __forceinline__ void epi_group8(const GemmArgs& g, int row, int col, 
         }
     }
 }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int BK, int AMODE, int EPI>
 __global__ void __launch_bounds__(256, 1)
@@ -179,6 +245,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_gate = s_bias + 256;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -269,13 +337,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         const int quad = warp & 3;
+        const int et = threadIdx.x - 128;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool gate_in_smem = (EPI == EPI_GATED) && (g.rows_per_batch % 128 == 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            const int n0 = n_blk * BN;
+            // stage this tile's bias (and gate) while the MMAs of the tile are still running
+            epi_bar_sync();
+            for (int c = et; c < BN; c += 128) {
+                const int col = n0 + c;
+                s_bias[c] = (g.bias != nullptr && col < g.N) ? __half2float(g.bias[col]) : 0.f;
+                if constexpr (EPI == EPI_GATED) {
+                    if (gate_in_smem) {
+                        const int b = ((m_blk * 128) / g.rows_per_batch) % g.gate_batches;
+                        s_gate[c] = col < g.N ? __half2float(g.gate[static_cast<size_t>(b) * g.gate_bstride + col]) : 0.f;
+                    }
+                }
+            }
+            epi_bar_sync();
+            const int row = m_blk * 128 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            HeadCursor hc{0, 0, 0};
+            size_t head_row_off = 0;
+            if constexpr (EPI == EPI_HEADS) {
+                hc.which = n0 / g.split_cols;
+                const int c = n0 - hc.which * g.split_cols;
+                hc.head = c / g.Dh;
+                hc.d = c - hc.head * g.Dh;
+                const int b = row / g.Nseq;
+                head_row_off = (static_cast<size_t>(b) * g.H * g.Nseq + (row - b * g.Nseq)) * g.DhP;
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * 128 + quad * 32 + lane;
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
             constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -284,13 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, r);
                 else tmem_ld_32x16(taddr + c0, r);
                 tmem_ld_wait();
-                if (row < g.M) {
-#pragma unroll
-                    for (int j = 0; j < CH; j += 8) {
-                        const int col = n_blk * BN + c0 + j;
-                        if (col < g.N) epi_group8<EPI>(g, row, col, &r[j]);
-                    }
-                }
+                epi_chunk<EPI, CH>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
