@@ -1,0 +1,310 @@
+// tcgen05 flash attention for head_dim 72 (padded to 80):  out = softmax(q k^T * scale) v
+//   (contract of xformers.ops.memory_efficient_attention as called at models/attention.py:54,109)
+//
+// One CTA = 256 query rows (two 128-row tiles A/B) of one (batch, head); K / V^T stream through a 2-stage TMA ring
+// in 128-key tiles shared by both query tiles.
+//   warp 0      TMA producer (Q once, then K and V^T tiles; mbarrier complete_tx)
+//   warp 1      MMA issuer   (one thread):  S_X = Q_X K^T  (128x128x80, fp32 in TMEM),  O_X(j) = P_X V  (128x80x128)
+//   warp 2      TMEM allocator (512 columns: S_A, S_B, O_A, O_B)
+//   warps 4-7   softmax warpgroup of tile A, warps 8-11 of tile B: ONE THREAD PER QUERY ROW (TMEM lane == row), so the
+//               row max / row sum need no shuffles; P is written to shared memory as fp16 in the 128B-swizzled K-major
+//               layout the PV MMA reads; the running output lives in registers: o = o * alpha + tcgen05.ld(O_X(j)).
+// While warpgroup A does softmax on tile j the tensor core runs S_B(j) / PV; S_X(j+1) is issued as soon as warpgroup X
+// has drained S_X(j), so MMA, TMA and the exponentials overlap without a correction pass over TMEM.
+//
+// Layouts: q, k  [B,H,N,80] fp16 (d >= 72 zero);  vT [B,H,80,NkPad] fp16 (V transposed: keys contiguous, NkPad % 8 == 0,
+// rows d >= 72 and key columns >= Nk finite/zero);  out [B,Nq,H*72] fp16.
+#include "kernels.cuh"
+
+namespace tpx {
+
+namespace {
+
+constexpr int TA_DHP = 80;
+constexpr int TA_BQ = 128, TA_BKV = 128;
+constexpr int TA_Q_BYTES = 128 * 128 + 128 * 32;        // 64-wide SW128 part + 16-wide SW32 part
+constexpr int TA_K_BYTES = TA_Q_BYTES;
+constexpr int TA_VBOX_BYTES = TA_DHP * 128;             // 80 rows x 64 keys
+constexpr int TA_V_BYTES = 2 * TA_VBOX_BYTES;
+constexpr int TA_P_BYTES = 2 * 128 * 128;
+constexpr int TA_KV_STAGE = TA_K_BYTES + TA_V_BYTES;
+constexpr int TA_OFF_Q = 0;
+constexpr int TA_OFF_KV = 2 * TA_Q_BYTES;
+constexpr int TA_OFF_P = TA_OFF_KV + 2 * TA_KV_STAGE;
+constexpr int TA_OFF_BAR = TA_OFF_P + 2 * TA_P_BYTES;
+constexpr int TA_SMEM = TA_OFF_BAR + 256 + 1024;
+constexpr int TA_THREADS = 384;
+static_assert(TA_Q_BYTES % 1024 == 0 && TA_VBOX_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(TA_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
+                    const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
+                    int Dh, float scale_log2) {
+    extern __shared__ uint8_t ta_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TA_OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_full = bars + 5;        // 2 (per query tile)
+    uint64_t* s_free = bars + 7;        // 2
+    uint64_t* p_full = bars + 9;        // 2
+    uint64_t* o_full = bars + 11;       // 2
+    uint64_t* o_free = bars + 13;       // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (2 * TA_BQ);
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int bh = b * H + h;
+    const int nkt = (Nk + TA_BKV - 1) / TA_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQa); tma_prefetch_desc(&tmQb); tma_prefetch_desc(&tmKa); tma_prefetch_desc(&tmKb); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_free[i], 128);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * TA_Q_BYTES);
+            for (int X = 0; X < 2; ++X) {
+                uint8_t* qs = smem + TA_OFF_Q + X * TA_Q_BYTES;
+                const int row = bh * Nq + q0 + X * TA_BQ;
+                tma_load_2d(qs, &tmQa, q_full, 0, row);
+                tma_load_2d(qs + 128 * 128, &tmQb, q_full, 64, row);
+            }
+            for (int j = 0; j < nkt; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                uint8_t* ks = smem + TA_OFF_KV + s * TA_KV_STAGE;
+                uint8_t* vs = ks + TA_K_BYTES;
+                mbar_arrive_expect_tx(&kv_full[s], TA_KV_STAGE);
+                const int krow = bh * Nk + j * TA_BKV;
+                tma_load_2d(ks, &tmKa, &kv_full[s], 0, krow);
+                tma_load_2d(ks + 128 * 128, &tmKb, &kv_full[s], 64, krow);
+                tma_load_2d(vs, &tmV, &kv_full[s], j * TA_BKV, bh * TA_DHP);
+                tma_load_2d(vs + TA_VBOX_BYTES, &tmV, &kv_full[s], j * TA_BKV + 64, bh * TA_DHP);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
+            const uint32_t sbase = smem_u32(smem);
+            auto issue_qk = [&](int X, int s) {
+                const uint32_t qa = sbase + TA_OFF_Q + X * TA_Q_BYTES, ka = sbase + TA_OFF_KV + s * TA_KV_STAGE;
+                const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
+                const uint32_t ts = tmem_base + X * 128;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(ts, dq + 2 * i, dk + 2 * i, idesc_qk, i > 0 ? 1u : 0u);
+                umma_f16(ts, umma_desc_kmajor<32>(qa + 128 * 128), umma_desc_kmajor<32>(ka + 128 * 128), idesc_qk, 1u);
+                umma_commit(&s_full[X]);
+            };
+            auto issue_pv = [&](int X, int s) {
+                const uint32_t pa = sbase + TA_OFF_P + X * TA_P_BYTES, va = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES;
+                const uint32_t to = tmem_base + 256 + X * 128;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t dp = umma_desc_kmajor<128>(pa + kb * 128 * 128), dv = umma_desc_kmajor<128>(va + kb * TA_VBOX_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) umma_f16(to, dp + 2 * i, dv + 2 * i, idesc_pv, (kb | i) != 0 ? 1u : 0u);
+                }
+                umma_commit(&o_full[X]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_qk(0, 0);
+            issue_qk(1, 0);
+            for (int j = 0; j < nkt; ++j) {
+                const int s = j & 1;
+                for (int X = 0; X < 2; ++X) {
+                    if (j + 1 < nkt) {
+                        if (X == 0) mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&s_free[X], j & 1);
+                        tc_fence_after();
+                        issue_qk(X, (j + 1) & 1);
+                    }
+                    mbar_wait(&p_full[X], j & 1);
+                    if (j > 0) mbar_wait(&o_free[X], (j - 1) & 1);
+                    tc_fence_after();
+                    issue_pv(X, s);
+                }
+                umma_commit(&kv_empty[s]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int X = (warp - 4) >> 2;               // query tile of this warpgroup
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;              // row in the tile == TMEM lane
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t tS = tmem_base + X * 128 + lane_off;
+        const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
+        uint8_t* pS = smem + TA_OFF_P + X * TA_P_BYTES + r * 128;
+        const int sw = r & 7;
+        float o[TA_DHP];
+#pragma unroll
+        for (int i = 0; i < TA_DHP; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+        auto accumulate_o = [&](float a) {
+            uint32_t t[32];
+            tmem_ld_32x32(tO, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], a, __uint_as_float(t[i]));
+            tmem_ld_32x32(tO + 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], a, __uint_as_float(t[i]));
+            tmem_ld_32x16(tO + 64, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[64 + i] = fmaf(o[64 + i], a, __uint_as_float(t[i]));
+        };
+        for (int j = 0; j < nkt; ++j) {
+            const int nvalid = Nk - j * TA_BKV;      // keys of this tile that exist (>= 1)
+            mbar_wait(&s_full[X], j & 1);
+            tc_fence_after();
+            // ---- pass 1: row max ----
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t t[32];
+                tmem_ld_32x32(tS + c * 32, t);
+                tmem_ld_wait();
+                if (nvalid >= (c + 1) * 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(t[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(t[i]));
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = ex2((m_run - m_new) * scale_log2);
+            const float msc = m_new * scale_log2;
+            // ---- fold the previous tile's P V into the running output (its MMA ran while we waited for S) ----
+            if (j > 0) {
+                mbar_wait(&o_full[X], (j - 1) & 1);
+                tc_fence_after();
+                accumulate_o(alpha_prev);
+                tc_fence_before();
+                mbar_arrive(&o_free[X]);
+            }
+            alpha_prev = alpha;
+            // ---- pass 2: p = exp2(s*scale - m*scale) -> fp16 -> swizzled smem ; row sum ----
+            float rs = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t t[32];
+                tmem_ld_32x32(tS + c * 32, t);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
+                    float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
+                    if (c * 32 + i >= nvalid) p0 = 0.f;
+                    if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+                    rs += p0 + p1;
+                    __half2 hh = __floats2half2_rn(p0, p1);
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                uint8_t* dst = pS + (c >> 1) * (128 * 128);
+                const int cc0 = (c & 1) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+            m_run = m_new;
+            l_run = l_run * alpha + rs;
+            tc_fence_before();
+            mbar_arrive(&s_free[X]);        // S_X drained: the next Q K^T may overwrite it
+            fence_proxy_async();            // make the P stores visible to the tensor core (async proxy)
+            mbar_arrive(&p_full[X]);
+        }
+        mbar_wait(&o_full[X], (nkt - 1) & 1);
+        tc_fence_after();
+        accumulate_o(alpha_prev);
+        const int row = q0 + X * TA_BQ + r;
+        if (row < Nq) {
+            const float inv = 1.0f / l_run;
+            __half* orow = out + (static_cast<size_t>(b) * Nq + row) * (H * Dh) + h * Dh;
+#pragma unroll
+            for (int d = 0; d < TA_DHP; d += 8) {
+                if (d < Dh) {
+                    Pack8 v;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn(o[d + i] * inv);
+                    *reinterpret_cast<uint4*>(orow + d) = v.u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
+                        cudaStream_t st) {
+    TPX_CHECK(B > 0 && H > 0 && Nq > 0 && Nk > 0, TPX_ERR_SHAPE, "attention_tc: empty problem");
+    TPX_CHECK(Dh % 8 == 0 && Dh <= TA_DHP && Dh > 64, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers 64 < Dh <= 80)", Dh);
+    TPX_CHECK(NkPad % 8 == 0 && NkPad >= Nk, TPX_ERR_SHAPE, "attention_tc: NkPad %d must be a multiple of 8 and >= Nk %d", NkPad, Nk);
+    TPX_CHECK(H <= 65535 && B <= 65535, TPX_ERR_SHAPE, "attention_tc: grid too large");
+    CUtensorMap mQa, mQb, mKa, mKb, mV;
+    int rc;
+    const long long qrows = static_cast<long long>(B) * H * Nq, krows = static_cast<long long>(B) * H * Nk;
+    if ((rc = make_tensor_map_2d(q, qrows, TA_DHP, TA_DHP, 128, 64, &mQa)) != TPX_OK) return rc;
+    if ((rc = make_tensor_map_2d(q, qrows, TA_DHP, TA_DHP, 128, 16, &mQb)) != TPX_OK) return rc;
+    if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 64, &mKa)) != TPX_OK) return rc;
+    if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 16, &mKb)) != TPX_OK) return rc;
+    if ((rc = make_tensor_map_2d(vT, static_cast<long long>(B) * H * TA_DHP, NkPad, NkPad, TA_DHP, 64, &mV)) != TPX_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        attr_set = true;
+    }
+    ProfScope prof(PROF_ATTENTION, st);
+    dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
+    attention_tc_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f);
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
+}  // namespace tpx

@@ -29,7 +29,8 @@ struct tpx_dit {
     bool finalized = false;
     // conditioning store
     __half *ck = nullptr, *cv = nullptr, *y16 = nullptr;
-    int cond_n = 0, cond_M = 0;
+    int cond_n = 0, cond_M = 0, cond_MP = 0;
+    bool tc_attn = false;                 // tcgen05 attention (64 < Dh <= 80, N % 8 == 0); V kept transposed
 };
 
 static size_t al8(size_t n) { return (n + 7) & ~static_cast<size_t>(7); }
@@ -231,6 +232,7 @@ int tpx_dit_create(const tpx_dit_config* c, tpx_dit** out) {
     h->D = c->hidden_size; h->L = c->depth; h->H = c->num_heads; h->Dm = c->mlp_hidden; h->Dh = Dh;
     h->DhP = Dh <= 16 ? 16 : (Dh <= 32 ? 32 : (Dh <= 64 ? 64 : (Dh <= 80 ? 80 : 128)));
     h->Ltot = h->L * 9 * h->D + 2 * h->D;
+    h->tc_attn = (h->DhP == 80 && h->Dh > 64 && h->N % 8 == 0);
     carve_store(h, nullptr);
     cudaError_t e = cudaMalloc(&h->store, h->store_halves * 2);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(parameter store)"); }
@@ -286,7 +288,8 @@ int tpx_dit_finalize(tpx_dit* h, void* stream) {
 
 size_t tpx_dit_cond_bytes(const tpx_dit* h, int n_cross, int M) {
     if (h == nullptr || n_cross <= 0 || M <= 0) return 0;
-    const size_t kv = static_cast<size_t>(h->L) * n_cross * h->H * M * h->DhP * 2;
+    const int MP = (M + 7) & ~7;   // key count padded for the transposed V (TMA row pitch must be a multiple of 16 B)
+    const size_t kv = static_cast<size_t>(h->L) * n_cross * h->H * MP * h->DhP * 2;
     const size_t y = (static_cast<size_t>(n_cross) * M * h->Dc * 2 + 255) & ~static_cast<size_t>(255);
     return 2 * ((kv + 255) & ~static_cast<size_t>(255)) + y;
 }
@@ -304,23 +307,28 @@ int tpx_dit_set_cond(tpx_dit* h, const float* y, int n_cross, int M, void* cond_
               tpx_dit_cond_bytes(h, n_cross, M));
     TPX_CHECK((reinterpret_cast<uintptr_t>(cond_ws) & 255) == 0, TPX_ERR_ARG, "dit_set_cond: store must be 256-B aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t kv = (static_cast<size_t>(h->L) * n_cross * h->H * M * h->DhP * 2 + 255) & ~static_cast<size_t>(255);
+    const int MP = (M + 7) & ~7;
+    const size_t kv = (static_cast<size_t>(h->L) * n_cross * h->H * MP * h->DhP * 2 + 255) & ~static_cast<size_t>(255);
     uint8_t* base = static_cast<uint8_t*>(cond_ws);
     h->ck = reinterpret_cast<__half*>(base);
     h->cv = reinterpret_cast<__half*>(base + kv);
     h->y16 = reinterpret_cast<__half*>(base + 2 * kv);
     h->cond_n = n_cross;
     h->cond_M = M;
+    h->cond_MP = MP;
+    if (h->tc_attn) TPX_CUDA(cudaMemsetAsync(h->cv, 0, kv, st));   // key columns [M, MP) of the transposed V must be finite
     int rc = launch_to_half(y, TPX_DTYPE_F32, h->y16, static_cast<long long>(n_cross) * M * h->Dc, st);
     if (rc != TPX_OK) return rc;
     const size_t per_layer = static_cast<size_t>(n_cross) * h->H * M * h->DhP;
+    const size_t per_layer_v = h->tc_attn ? static_cast<size_t>(n_cross) * h->H * MP * h->DhP : per_layer;
     for (int i = 0; i < h->L; ++i) {
         GemmArgs a{};
         a.bias = h->layers[i].bkv;
         a.post_scale = 1.0f;
         a.out0 = h->ck + i * per_layer;
-        a.out1 = h->cv + i * per_layer;
+        a.out1 = h->cv + i * per_layer_v;
         a.split_cols = h->D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = M;
+        if (h->tc_attn) { a.vt_which_plus1 = 2; a.vt_ld = MP; }
         rc = gemm_linear(h->y16, h->Dc, h->layers[i].Wkv, n_cross * M, 2 * h->D, h->Dc, EPI_HEADS, a, 0, st);
         if (rc != TPX_OK) return rc;
     }
@@ -355,6 +363,7 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     TPX_RC(launch_x_embed(x, h->Wx, h->bx, B * N, h->Cin, D, w.xres, use_cfg ? static_cast<long long>(B) * N * D : 0, st));
 
     const size_t per_layer_kv = static_cast<size_t>(h->cond_n) * h->H * M * h->DhP;
+    const size_t per_layer_v = h->tc_attn ? static_cast<size_t>(h->cond_n) * h->H * h->cond_MP * h->DhP : per_layer_kv;
     for (int i = 0; i < h->L; ++i) {
         const DitLayer& l = h->layers[i];
         const __half* mod = w.mod + static_cast<size_t>(i) * 9 * D;   // (shift,scale,gate) x (mca,msa,mlp)
@@ -366,7 +375,8 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
             a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N;
             TPX_RC(gemm_linear(w.h16, D, l.Wq, Sc * N, D, D, EPI_HEADS, a, 0, st));
         }
-        TPX_RC(launch_attention(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_kv, w.ao, Sc, h->H, N, M, h->Dh, h->DhP, qscale, st));
+        if (h->tc_attn) TPX_RC(launch_attention_tc(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_v, w.ao, Sc, h->H, N, M, h->cond_MP, h->Dh, qscale, st));
+        else TPX_RC(launch_attention(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_kv, w.ao, Sc, h->H, N, M, h->Dh, h->DhP, qscale, st));
         {
             GemmArgs a{};
             a.bias = l.bcp; a.post_scale = 1.0f; a.xres = w.xres; a.ldx = D;
@@ -380,9 +390,11 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
             GemmArgs a{};
             a.bias = l.bqkv; a.post_scale = 1.0f; a.out0 = w.q; a.out1 = w.k; a.out2 = w.v;
             a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N;
+            if (h->tc_attn) { a.vt_which_plus1 = 3; a.vt_ld = N; }
             TPX_RC(gemm_linear(w.h16, D, l.Wqkv, S * N, 3 * D, D, EPI_HEADS, a, 0, st));
         }
-        TPX_RC(launch_attention(w.q, w.k, w.v, w.ao, S, h->H, N, N, h->Dh, h->DhP, qscale, st));
+        if (h->tc_attn) TPX_RC(launch_attention_tc(w.q, w.k, w.v, w.ao, S, h->H, N, N, N, h->Dh, qscale, st));
+        else TPX_RC(launch_attention(w.q, w.k, w.v, w.ao, S, h->H, N, N, h->Dh, h->DhP, qscale, st));
         {
             GemmArgs a{};
             a.bias = l.bsp; a.post_scale = 1.0f; a.xres = w.xres; a.ldx = D;
@@ -460,7 +472,7 @@ int tpx_linear_gated(const void* A, int lda, const void* W, const void* bias, co
 }
 
 int tpx_linear_heads(const void* A, int lda, const void* W, const void* bias, void* out0, void* out1, void* out2, int M, int N, int K, int split_cols,
-                     int H, int Dh, int DhP, int n_seq_tokens, float post_scale, int tile_n, void* stream) {
+                     int H, int Dh, int DhP, int n_seq_tokens, float post_scale, int tile_n, int transposed_which, int transposed_ld, void* stream) {
     TPX_CHECK(A != nullptr && W != nullptr && out0 != nullptr, TPX_ERR_ARG, "linear_heads: null argument");
     TPX_CHECK(Dh % 8 == 0 && DhP % 8 == 0 && DhP >= Dh && split_cols == H * Dh && N % split_cols == 0, TPX_ERR_SHAPE, "linear_heads: bad head geometry");
     int rc = tpx_device_check();
@@ -469,6 +481,8 @@ int tpx_linear_heads(const void* A, int lda, const void* W, const void* bias, vo
     a.bias = static_cast<const __half*>(bias); a.post_scale = post_scale;
     a.out0 = static_cast<__half*>(out0); a.out1 = static_cast<__half*>(out1); a.out2 = static_cast<__half*>(out2);
     a.split_cols = split_cols; a.Dh = Dh; a.DhP = DhP; a.H = H; a.Nseq = n_seq_tokens;
+    a.vt_which_plus1 = transposed_which >= 0 ? transposed_which + 1 : 0;
+    a.vt_ld = transposed_ld;
     return gemm_linear(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), M, N, K, EPI_HEADS, a, tile_n, static_cast<cudaStream_t>(stream));
 }
 
@@ -485,6 +499,14 @@ int tpx_attention(const void* q, const void* k, const void* v, void* out, int B,
     TPX_CHECK(q != nullptr && k != nullptr && v != nullptr && out != nullptr, TPX_ERR_ARG, "attention: null argument");
     return launch_attention(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v), static_cast<__half*>(out), B, H,
                             Nq, Nk, Dh, DhP, scale, static_cast<cudaStream_t>(stream));
+}
+
+int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale, void* stream) {
+    TPX_CHECK(q != nullptr && k != nullptr && vT != nullptr && out != nullptr, TPX_ERR_ARG, "attention_tc: null argument");
+    int rc = tpx_device_check();
+    if (rc != TPX_OK) return rc;
+    return launch_attention_tc(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(vT), static_cast<__half*>(out), B, H,
+                               Nq, Nk, NkPad, Dh, scale, static_cast<cudaStream_t>(stream));
 }
 
 int tpx_cfg_combine(const void* both, int64_t n_half, float s, void* out, void* stream) {

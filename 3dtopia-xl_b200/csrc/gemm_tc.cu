@@ -97,7 +97,9 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
+static CUtensorMapSwizzle swizzle_for(int bk) {
+    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
 
 using MapKey = std::tuple<const void*, long long, long long, long long, int, int, int>;
 static std::map<MapKey, CUtensorMap> g_maps;
@@ -147,6 +149,10 @@ static int map_conv(const void* ptr, long long P, int S, int C, int bk, CUtensor
     g_maps[key] = m;
     *out = m;
     return TPX_OK;
+}
+
+int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out) {
+    return map_2d(ptr, rows, cols, ld, box_rows, box_cols, out);
 }
 
 template <int BN, int BK, int AMODE, int EPI>

@@ -36,6 +36,7 @@ struct GemmArgs {
     __half* out2;
     int ldo;
     int split_cols, Dh, DhP, H, Nseq;
+    int vt_which_plus1, vt_ld;   // EPI_HEADS: column group (which+1) stored TRANSPOSED as [b,head,DhP,vt_ld] (keys contiguous); 0 = none
     float* xres;
     int ldx;
     const __half* gate;
@@ -84,6 +85,7 @@ union Pack8 {
 // incrementally instead of divided out per group.
 struct HeadCursor {
     int which, head, d;
+    int b, n;   // batch / token of this thread's row
 };
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
@@ -129,19 +131,30 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const float* __rest
 #pragma unroll
         for (int j = 0; j < NG; ++j) {
             __half* base = hc.which == 0 ? g.out0 : (hc.which == 1 ? g.out1 : g.out2);
-            __half* dst = base + head_row_off + static_cast<size_t>(hc.head) * g.Nseq * g.DhP + hc.d;
-            Pack8 o;
             const bool sc = g.post_scale != 1.0f && hc.which == 0;
+            Pack8 o;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float x = h2f_round(v[j * 8 + i]);
                 if (sc) x = x * g.post_scale;
                 o.h[i] = __float2half_rn(x);
             }
-            if (ok[j]) {
-                *reinterpret_cast<uint4*>(dst) = o.u;
-                if (hc.d + 8 == g.Dh)   // last real group of this head: write the zero padding d in [Dh, DhP)
-                    for (int p = g.Dh; p < g.DhP; p += 8) *reinterpret_cast<uint4*>(dst + (p - hc.d)) = make_uint4(0, 0, 0, 0);
+            if (hc.which + 1 == g.vt_which_plus1) {
+                // transposed store for the tcgen05 attention's PV operand: [b, head, d, token] (tokens contiguous)
+                __half* dst = base + (static_cast<size_t>(hc.b * g.H + hc.head) * g.DhP + hc.d) * g.vt_ld + hc.n;
+                if (ok[j]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[static_cast<size_t>(i) * g.vt_ld] = o.h[i];
+                    if (hc.d + 8 == g.Dh)
+                        for (int p = g.Dh; p < g.DhP; ++p) dst[static_cast<size_t>(p - hc.d) * g.vt_ld] = __float2half_rn(0.f);
+                }
+            } else {
+                __half* dst = base + head_row_off + static_cast<size_t>(hc.head) * g.Nseq * g.DhP + hc.d;
+                if (ok[j]) {
+                    *reinterpret_cast<uint4*>(dst) = o.u;
+                    if (hc.d + 8 == g.Dh)   // last real group of this head: write the zero padding d in [Dh, DhP)
+                        for (int p = g.Dh; p < g.DhP; p += 8) *reinterpret_cast<uint4*>(dst + (p - hc.d)) = make_uint4(0, 0, 0, 0);
+                }
             }
             hc.d += 8;
             if (hc.d >= g.Dh) {
@@ -359,15 +372,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             epi_bar_sync();
             const int row = m_blk * 128 + quad * 32 + lane;
             const bool row_ok = row < g.M;
-            HeadCursor hc{0, 0, 0};
+            HeadCursor hc{0, 0, 0, 0, 0};
             size_t head_row_off = 0;
             if constexpr (EPI == EPI_HEADS) {
                 hc.which = n0 / g.split_cols;
                 const int c = n0 - hc.which * g.split_cols;
                 hc.head = c / g.Dh;
                 hc.d = c - hc.head * g.Dh;
-                const int b = row / g.Nseq;
-                head_row_off = (static_cast<size_t>(b) * g.H * g.Nseq + (row - b * g.Nseq)) * g.DhP;
+                hc.b = row / g.Nseq;
+                hc.n = row - hc.b * g.Nseq;
+                head_row_off = (static_cast<size_t>(hc.b) * g.H * g.Nseq + hc.n) * g.DhP;
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();

@@ -34,6 +34,12 @@ int launch_fill_rows_half(const __half* vec, __half* dst, long long rows, int K,
 int launch_attention(const __half* q, const __half* k, const __half* v, __half* out, int B, int H, int Nq, int Nk, int Dh, int DhP, float scale,
                      cudaStream_t st);
 
+// attention_tc.cu : tcgen05 version for 64 < Dh <= 80; vT is V transposed [B,H,80,NkPad]
+int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
+                        cudaStream_t st);
+// gemm_tc.cu : cached 2-D TMA descriptor over a row-major fp16 matrix (swizzle = box_cols * 2 bytes: 128/64/32)
+int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out);
+
 // vae_kernels.cu
 int launch_vae_conv_in(const void* z, int z_dtype, const __half* w_pq, const __half* b_pq, const __half* W, const __half* bias, int P, int C,
                        __half* out, cudaStream_t st);

@@ -133,14 +133,19 @@ int tpx_linear(const void* A_f16, int lda, const void* W_f16, const void* bias_f
 int tpx_linear_gated(const void* A_f16, int lda, const void* W_f16, const void* bias_f16, const void* gate_f16, int gate_bstride, int gate_batches,
                      int rows_per_batch, float* xres, int ldx, int M, int N, int K, int tile_n, void* stream);
 /* Column-split + head-split store: col -> (which = col / split_cols, head, d); row -> (b = row / n_seq_tokens, n);
- * out{which}[b, head, n, DhP] (zero padded).  post_scale applies to which == 0 (attention.py:105). */
+ * out{which}[b, head, n, DhP] (zero padded).  post_scale applies to which == 0 (attention.py:105).  The column group
+ * `transposed_which` (-1 = none) is stored transposed as [b, head, DhP, transposed_ld] (tokens contiguous): the V operand
+ * layout of tpx_attention_tc. */
 int tpx_linear_heads(const void* A_f16, int lda, const void* W_f16, const void* bias_f16, void* out0, void* out1, void* out2, int M, int N, int K,
-                     int split_cols, int H, int Dh, int DhP, int n_seq_tokens, float post_scale, int tile_n, void* stream);
+                     int split_cols, int H, int Dh, int DhP, int n_seq_tokens, float post_scale, int tile_n, int transposed_which, int transposed_ld,
+                     void* stream);
 /* y = LN(x; eps) * h(1 + scale) + shift -> fp16   (modulate(norm(x), shift, scale), utils.py:19-20) */
 int tpx_ln_modulate(float* x, int rows, int D, float eps, const void* shift_f16, const void* scale_f16, int mod_bstride, int rows_per_batch,
                     int mod_batches, void* out_f16, const void* pre_gate_f16, const void* pre_const_f16, int pre_row0, void* stream);
 /* memory_efficient_attention contract (attention.py:54,109): q [B,H,Nq,DhP], k/v [B,H,Nk,DhP] -> out [B,Nq,H*Dh] */
 int tpx_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int Dh, int DhP, float scale, void* stream);
+/* Same contract on the tcgen05 path (64 < Dh <= 80): q,k [B,H,N,80]; vT = V transposed [B,H,80,NkPad], NkPad % 8 == 0. */
+int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale, void* stream);
 /* out = h(uncond + h(s * h(cond - uncond)))  over [cond; uncond] halves of n_half elements (dit_crossattn.py:210-213) */
 int tpx_cfg_combine(const void* both_f16, int64_t n_half, float s, void* out_f16, void* stream);
 /* GroupNorm(groups, eps, affine) [+ SiLU] on a channels-last fp16 volume [P, S3, C]  (vae3d_dib.py:109,112,131-139) */

@@ -42,3 +42,26 @@ def test_attention_uniform_when_keys_identical():
     ref = vrow[..., :Dh].permute(0, 2, 1, 3).reshape(B, 1, H * Dh).expand(B, Nq, H * Dh)
     torch.cuda.synchronize()
     assert (out.float() - ref.float()).abs().max() <= 1e-3 * ref.float().abs().max()
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 16, 2048, 2048), (1, 16, 2048, 1370), (1, 2, 256, 128), (2, 3, 300, 77), (1, 4, 128, 1000), (1, 1, 513, 257)])
+def test_attention_tcgen05(B, H, Nq, Nk):
+    """tcgen05 path (Dh 72 -> 80): V given transposed [B,H,80,NkPad]; ragged query and key counts."""
+    Dh, DhP = 72, 80
+    NkPad = (Nk + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(Nq * 7 + Nk)
+    def mk(n):
+        t = torch.zeros(B, H, n, DhP, dtype=torch.float16, device="cuda")
+        t[..., :Dh] = torch.randn(B, H, n, Dh, generator=g, device="cuda").half()
+        return t
+    q, k, v = mk(Nq), mk(Nk), mk(Nk)
+    vT = torch.zeros(B, H, DhP, NkPad, dtype=torch.float16, device="cuda")
+    vT[..., :Nk] = v.transpose(-1, -2)
+    out = torch.full((B, Nq, H * Dh), 9.0, dtype=torch.float16, device="cuda")
+    scale = Dh ** -0.5
+    _lib.check(_lib.lib().tpx_attention_tc(q.data_ptr(), k.data_ptr(), vT.data_ptr(), out.data_ptr(), B, H, Nq, Nk, NkPad, Dh, scale, st()))
+    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    ref = torch.matmul(torch.softmax(s, -1), v.float())[..., :Dh].permute(0, 2, 1, 3).reshape(B, Nq, H * Dh)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 2e-3
+    assert (out.float() - ref).abs().max() < 2e-2

@@ -47,7 +47,7 @@ def test_linear_heads_layout_and_padding():
     A, W, b = _rand(B * N, K, seed=8), _rand(3 * D, K, scale=1 / 16, seed=9), _rand(3 * D, seed=10)
     outs = [torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
     _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
-                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, 0, st()))
+                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, 0, -1, 0, st()))
     ref = linear_ref(A, W, b).reshape(B, N, 3, H, Dh)
     torch.cuda.synchronize()
     for w in range(3):
@@ -67,3 +67,20 @@ def test_linear_gated_residual():
     ref = x0 + (gate[0, 2 * D:3 * D].float() * linear_ref(A, W, b).float()).half().float()
     torch.cuda.synchronize()
     assert (x - ref).abs().max() < 2e-2 and rel_l2(x, ref) < 1e-3
+
+
+def test_linear_heads_transposed_v():
+    """V stored as [b, head, DhP, tokens] for the tcgen05 attention's PV operand; zero rows for d >= Dh."""
+    B, N, H, Dh, DhP, K = 2, 256, 16, 72, 80, 256
+    D = H * Dh
+    A, W, b = _rand(B * N, K, seed=18), _rand(3 * D, K, scale=1 / 16, seed=19), _rand(3 * D, seed=20)
+    q = torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda")
+    k = torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda")
+    vT = torch.full((B, H, DhP, N), 7.0, dtype=torch.float16, device="cuda")
+    _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), q.data_ptr(), k.data_ptr(), vT.data_ptr(),
+                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, 0, 2, N, st()))
+    ref = linear_ref(A, W, b).reshape(B, N, 3, H, Dh)
+    torch.cuda.synchronize()
+    assert torch.all(vT[:, :, Dh:, :] == 0) and torch.all(k[..., Dh:] == 0)
+    assert rel_l2(vT[:, :, :Dh, :], ref[:, :, 2].permute(0, 2, 3, 1)) < 2e-3
+    assert rel_l2(q[..., :Dh], ref[:, :, 0].permute(0, 2, 1, 3)) < 2e-3
