@@ -90,6 +90,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
     // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464)
 
     if (warp == 0) {
@@ -229,15 +231,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 tmem_ld_32x32(tS + c * 32, t);
                 tmem_ld_wait();
                 uint32_t pk[16];
+                if (nvalid >= (c + 1) * 32) {           // whole chunk valid: no masking instructions
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
-                    float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
-                    if (c * 32 + i >= nvalid) p0 = 0.f;
-                    if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                    rs += p0 + p1;
-                    __half2 hh = __floats2half2_rn(p0, p1);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
+                        const float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
+                        rs += p0 + p1;
+                        __half2 hh = __floats2half2_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
+                        float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
+                        if (c * 32 + i >= nvalid) p0 = 0.f;
+                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+                        rs += p0 + p1;
+                        __half2 hh = __floats2half2_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
                 }
                 uint8_t* dst = pS + (c >> 1) * (128 * 128);
                 const int cc0 = (c & 1) * 4;
@@ -302,7 +315,7 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     }
     ProfScope prof(PROF_ATTENTION, st);
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    attention_tc_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f);
+    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

@@ -13,10 +13,12 @@ namespace tpx {
 // =====================================================================================================
 constexpr int LN_MAX_ITERS = 16;  // D <= 2048
 
-__global__ void __launch_bounds__(256) ln_modulate_kernel(float* __restrict__ x, int rows, int D, float eps, const __half* __restrict__ shift,
+__global__ void __launch_bounds__(128) ln_modulate_kernel(float* __restrict__ x, int rows, int D, float eps, const __half* __restrict__ shift,
                                                           const __half* __restrict__ scale, int mod_bstride, int rows_per_batch, int mod_batches,
                                                           __half* __restrict__ out, const __half* __restrict__ pre_gate,
                                                           const __half* __restrict__ pre_const, int pre_row0) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -42,6 +44,17 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(float* __restrict__ x,
                 *reinterpret_cast<float4*>(xr + c) = v[i];
             }
     }
+    // shift / scale loads are issued before the reductions so their L2 latency overlaps the shuffles
+    const __half* shp = shift + static_cast<size_t>(bm) * mod_bstride;
+    const __half* scp = scale + static_cast<size_t>(bm) * mod_bstride;
+    uint2 shv[LN_MAX_ITERS], scv[LN_MAX_ITERS];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_ITERS; ++i)
+        if (i < ni) {
+            const int c = (lane + 32 * i) * 4;
+            shv[i] = __ldg(reinterpret_cast<const uint2*>(shp + c));
+            scv[i] = __ldg(reinterpret_cast<const uint2*>(scp + c));
+        }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_ITERS; ++i)
@@ -55,15 +68,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(float* __restrict__ x,
             q += (a * a + b * b) + (c * c + d * d);
         }
     const float rstd = rsqrtf(warp_sum(q) / D + eps);
-    const __half* shp = shift + static_cast<size_t>(bm) * mod_bstride;
-    const __half* scp = scale + static_cast<size_t>(bm) * mod_bstride;
     __half* orow = out + static_cast<size_t>(row) * D;
 #pragma unroll
     for (int i = 0; i < LN_MAX_ITERS; ++i)
         if (i < ni) {
             const int c = (lane + 32 * i) * 4;
-            const __half2 sh0 = *reinterpret_cast<const __half2*>(shp + c), sh1 = *reinterpret_cast<const __half2*>(shp + c + 2);
-            const __half2 sc0 = *reinterpret_cast<const __half2*>(scp + c), sc1 = *reinterpret_cast<const __half2*>(scp + c + 2);
+            const __half2 sh0 = *reinterpret_cast<const __half2*>(&shv[i].x), sh1 = *reinterpret_cast<const __half2*>(&shv[i].y);
+            const __half2 sc0 = *reinterpret_cast<const __half2*>(&scv[i].x), sc1 = *reinterpret_cast<const __half2*>(&scv[i].y);
             const float m0 = h2f_round(1.0f + __low2float(sc0)), m1 = h2f_round(1.0f + __high2float(sc0));
             const float m2 = h2f_round(1.0f + __low2float(sc1)), m3 = h2f_round(1.0f + __high2float(sc1));
             const float y0 = (v[i].x - mean) * rstd * m0 + __low2float(sh0);
@@ -83,8 +94,8 @@ int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift
     TPX_CHECK(D % 128 == 0 && D <= 128 * LN_MAX_ITERS, TPX_ERR_SHAPE, "ln_modulate: hidden size %d must be a multiple of 128 and <= %d", D, 128 * LN_MAX_ITERS);
     if (rows <= 0) return TPX_OK;
     ProfScope prof(PROF_LN, st);
-    ln_modulate_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, D, eps, shift, scale, mod_bstride, rows_per_batch, mod_batches, out, pre_gate,
-                                                       pre_const, pre_row0);
+    TPX_CUDA(launch_pdl(ln_modulate_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, x, rows, D, eps, shift, scale, mod_bstride, rows_per_batch, mod_batches,
+                        out, pre_gate, pre_const, pre_row0));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

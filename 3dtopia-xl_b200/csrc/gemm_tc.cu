@@ -166,7 +166,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
     }
     const int tiles = ((a.M + 127) / 128) * ((a.N + BN - 1) / BN);
     const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+    TPX_CUDA(launch_pdl(kern, dim3(grid), dim3(256), Cfg::SMEM_BYTES, stream, ta, tb, a));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

@@ -288,6 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
+    pdl_wait();                // ... and ours ends here: the operands written by the previous kernel are now visible
 
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + 127) / 128;

@@ -43,6 +43,25 @@ struct ProfScope {
     cudaStream_t st;
 };
 
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (PDL).  The kernel MUST call pdl_wait() before its
+// first access to global memory that an earlier kernel in the stream may have written.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
@@ -59,6 +78,12 @@ __device__ __forceinline__ uint32_t elect_one() {
         : "=r"(pred));
     return pred;
 }
+
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// Every kernel launched through launch_pdl() runs its prologue (barrier init, TMEM alloc, descriptor prefetch)
+// while the previous kernel of the stream drains, then waits here before touching global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
