@@ -7,10 +7,15 @@
 //   warp 1      MMA issuer   (one thread):  S_X = Q_X K^T  (128x128x80, fp32 in TMEM),  O_X(j) = P_X V  (128x80x128)
 //   warp 2      TMEM allocator (512 columns: S_A, S_B, O_A, O_B)
 //   warps 4-7   softmax warpgroup of tile A, warps 8-11 of tile B: ONE THREAD PER QUERY ROW (TMEM lane == row), so the
-//               row max / row sum need no shuffles; P is written to shared memory as fp16 in the 128B-swizzled K-major
-//               layout the PV MMA reads; the running output lives in registers: o = o * alpha + tcgen05.ld(O_X(j)).
+//               row max / row sum need no shuffles.  The whole 128-wide score row is pulled into registers with four
+//               back-to-back tcgen05.ld (S is released to the tensor core immediately), P is written to shared memory
+//               as fp16 in the 128B-swizzled K-major layout the PV MMA reads, and O accumulates IN TMEM across key
+//               tiles.  The running max is allowed to go stale by up to 2^8 (p <= 256 fits fp16 comfortably); only
+//               when a row's max grows by more than that is O rescaled in TMEM (tcgen05.ld / mul / tcgen05.st), which
+//               is rare after the first tiles — no per-tile correction pass.
+//   setmaxnreg moves registers from the control warps (48) to the softmax warps (208) for the 128-register score row.
 // While warpgroup A does softmax on tile j the tensor core runs S_B(j) / PV; S_X(j+1) is issued as soon as warpgroup X
-// has drained S_X(j), so MMA, TMA and the exponentials overlap without a correction pass over TMEM.
+// has pulled S_X(j) into registers, so MMA, TMA and the exponentials overlap.
 //
 // Layouts: q, k  [B,H,N,80] fp16 (d >= 72 zero);  vT [B,H,80,NkPad] fp16 (V transposed: keys contiguous, NkPad % 8 == 0,
 // rows d >= 72 and key columns >= Nk finite/zero);  out [B,Nq,H*72] fp16.
@@ -30,7 +35,8 @@ constexpr int TA_P_BYTES = 2 * 128 * 128;
 constexpr int TA_KV_STAGE = TA_K_BYTES + TA_V_BYTES;
 constexpr int TA_OFF_Q = 0;
 constexpr int TA_OFF_KV = 2 * TA_Q_BYTES;
-constexpr int TA_OFF_P = TA_OFF_KV + 2 * TA_KV_STAGE;
+constexpr int TA_KV_STAGES = 3;
+constexpr int TA_OFF_P = TA_OFF_KV + TA_KV_STAGES * TA_KV_STAGE;
 constexpr int TA_OFF_BAR = TA_OFF_P + 2 * TA_P_BYTES;
 constexpr int TA_SMEM = TA_OFF_BAR + 256 + 1024;
 constexpr int TA_THREADS = 384;
@@ -42,21 +48,49 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// timeline probe (only when a debug buffer is passed): block 0, one thread per role writes (tag, clock) pairs
+#define TA_DBG(slot, tag)                                                                    \
+    do {                                                                                     \
+        if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {       \
+            const int _n = static_cast<int>(dbg[(slot) * 1024]);                             \
+            if (_n < 500) { dbg[(slot) * 1024 + 1 + 2 * _n] = (tag); dbg[(slot) * 1024 + 2 + 2 * _n] = clock64(); dbg[(slot) * 1024] = _n + 1; } \
+        }                                                                                    \
+    } while (0)
+
 __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                    int Dh, float scale_log2) {
+                    int Dh, float scale_log2, long long* __restrict__ dbg) {
     extern __shared__ uint8_t ta_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TA_OFF_BAR);
     uint64_t* q_full = bars;            // 1
-    uint64_t* kv_full = bars + 1;       // 2
-    uint64_t* kv_empty = bars + 3;      // 2
-    uint64_t* s_full = bars + 5;        // 2 (per query tile)
-    uint64_t* s_free = bars + 7;        // 2
-    uint64_t* p_full = bars + 9;        // 2
-    uint64_t* o_full = bars + 11;       // 2
-    uint64_t* o_free = bars + 13;       // 2
+    uint64_t* kv_full = bars + 1;       // TA_KV_STAGES
+    uint64_t* kv_empty = bars + 4;      // TA_KV_STAGES
+    uint64_t* s_full = bars + 7;        // 2 (per query tile)
+    uint64_t* s_free = bars + 9;        // 2
+    uint64_t* p_full = bars + 11;       // 2
+    uint64_t* o_full = bars + 13;       // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,14 +104,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TA_KV_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_free[i], 128);
             mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_free[i], 128);
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -94,8 +129,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
     pdl_wait();
     // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464)
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, 2 * TA_Q_BYTES);
             for (int X = 0; X < 2; ++X) {
                 uint8_t* qs = smem + TA_OFF_Q + X * TA_Q_BYTES;
@@ -103,9 +140,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 tma_load_2d(qs, &tmQa, q_full, 0, row);
                 tma_load_2d(qs + 128 * 128, &tmQb, q_full, 64, row);
             }
-            for (int j = 0; j < nkt; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkt; ++j) {
+            const int s = j % TA_KV_STAGES;
+            mbar_wait(&kv_empty[s], ((j / TA_KV_STAGES) & 1) ^ 1);
+            if (elect_one()) {
                 uint8_t* ks = smem + TA_OFF_KV + s * TA_KV_STAGE;
                 uint8_t* vs = ks + TA_K_BYTES;
                 mbar_arrive_expect_tx(&kv_full[s], TA_KV_STAGE);
@@ -115,55 +155,68 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 tma_load_2d(vs, &tmV, &kv_full[s], j * TA_BKV, bh * TA_DHP);
                 tma_load_2d(vs + TA_VBOX_BYTES, &tmV, &kv_full[s], j * TA_BKV + 64, bh * TA_DHP);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
-            constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
-            const uint32_t sbase = smem_u32(smem);
-            auto issue_qk = [&](int X, int s) {
-                const uint32_t qa = sbase + TA_OFF_Q + X * TA_Q_BYTES, ka = sbase + TA_OFF_KV + s * TA_KV_STAGE;
-                const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
-                const uint32_t ts = tmem_base + X * 128;
+        // warp-converged issuer (uniform control flow, one elected lane issues): descriptors stay in uniform registers
+        constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
+        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+        auto issue_qk = [&](int X, int s) {
+            const uint32_t qa = sbase + TA_OFF_Q + X * TA_Q_BYTES, ka = sbase + TA_OFF_KV + s * TA_KV_STAGE;
+            const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
+            const uint64_t dq2 = umma_desc_kmajor<32>(qa + 128 * 128), dk2 = umma_desc_kmajor<32>(ka + 128 * 128);
+            const uint32_t ts = tbase + X * 128;
+            if (elect_one()) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) umma_f16(ts, dq + 2 * i, dk + 2 * i, idesc_qk, i > 0 ? 1u : 0u);
-                umma_f16(ts, umma_desc_kmajor<32>(qa + 128 * 128), umma_desc_kmajor<32>(ka + 128 * 128), idesc_qk, 1u);
+                umma_f16(ts, dq2, dk2, idesc_qk, 1u);
                 umma_commit(&s_full[X]);
-            };
-            auto issue_pv = [&](int X, int s) {
-                const uint32_t pa = sbase + TA_OFF_P + X * TA_P_BYTES, va = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES;
-                const uint32_t to = tmem_base + 256 + X * 128;
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t dp = umma_desc_kmajor<128>(pa + kb * 128 * 128), dv = umma_desc_kmajor<128>(va + kb * TA_VBOX_BYTES);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) umma_f16(to, dp + 2 * i, dv + 2 * i, idesc_pv, (kb | i) != 0 ? 1u : 0u);
-                }
-                umma_commit(&o_full[X]);
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            issue_qk(0, 0);
-            issue_qk(1, 0);
-            for (int j = 0; j < nkt; ++j) {
-                const int s = j & 1;
-                for (int X = 0; X < 2; ++X) {
-                    if (j + 1 < nkt) {
-                        if (X == 0) mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                        mbar_wait(&s_free[X], j & 1);
-                        tc_fence_after();
-                        issue_qk(X, (j + 1) & 1);
-                    }
-                    mbar_wait(&p_full[X], j & 1);
-                    if (j > 0) mbar_wait(&o_free[X], (j - 1) & 1);
-                    tc_fence_after();
-                    issue_pv(X, s);
-                }
-                umma_commit(&kv_empty[s]);
             }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int X, int s, uint32_t acc_first) {
+            const uint32_t pa = sbase + TA_OFF_P + X * TA_P_BYTES, va = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES;
+            const uint32_t to = tbase + 256 + X * 128;
+            const uint64_t dp0 = umma_desc_kmajor<128>(pa), dv0 = umma_desc_kmajor<128>(va);
+            const uint64_t dp1 = umma_desc_kmajor<128>(pa + 128 * 128), dv1 = umma_desc_kmajor<128>(va + TA_VBOX_BYTES);
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(to, dp0 + 2 * i, dv0 + 2 * i, idesc_pv, i != 0 ? 1u : acc_first);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(to, dp1 + 2 * i, dv1 + 2 * i, idesc_pv, 1u);
+                umma_commit(&o_full[X]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        for (int j = 0; j < nkt; ++j) {
+            const int s = j % TA_KV_STAGES;
+            if (j + 1 < nkt) {           // next scores first: both softmax warpgroups get S(j+1) while they exponentiate tile j
+                const int sn = (j + 1) % TA_KV_STAGES;
+                mbar_wait(&kv_full[sn], ((j + 1) / TA_KV_STAGES) & 1);
+                for (int X = 0; X < 2; ++X) {
+                    mbar_wait(&s_free[X], j & 1);
+                    tc_fence_after();
+                    issue_qk(X, sn);
+                }
+            }
+            for (int X = 0; X < 2; ++X) {
+                mbar_wait(&p_full[X], j & 1);
+                tc_fence_after();
+                issue_pv(X, s, j > 0 ? 1u : 0u);      // O_X accumulates in TMEM across key tiles
+            }
+            if (elect_one()) umma_commit(&kv_empty[s]);
+            __syncwarp();
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int X = (warp - 4) >> 2;               // query tile of this warpgroup
         const int quad = warp & 3;
         const int r = quad * 32 + lane;              // row in the tile == TMEM lane
@@ -172,112 +225,142 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
         uint8_t* pS = smem + TA_OFF_P + X * TA_P_BYTES + r * 128;
         const int sw = r & 7;
-        float o[TA_DHP];
-#pragma unroll
-        for (int i = 0; i < TA_DHP; ++i) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-        auto accumulate_o = [&](float a) {
-            uint32_t t[32];
-            tmem_ld_32x32(tO, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], a, __uint_as_float(t[i]));
-            tmem_ld_32x32(tO + 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], a, __uint_as_float(t[i]));
-            tmem_ld_32x16(tO + 64, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[64 + i] = fmaf(o[64 + i], a, __uint_as_float(t[i]));
-        };
+        float m_ref = 0.f, l_run = 0.f;
         for (int j = 0; j < nkt; ++j) {
             const int nvalid = Nk - j * TA_BKV;      // keys of this tile that exist (>= 1)
+            if (r == 0) TA_DBG(X, 1);
             mbar_wait(&s_full[X], j & 1);
             tc_fence_after();
-            // ---- pass 1: row max ----
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t t[32];
-                tmem_ld_32x32(tS + c * 32, t);
-                tmem_ld_wait();
-                if (nvalid >= (c + 1) * 32) {
+            if (r == 0) TA_DBG(X, 2);
+            uint32_t sv[128];
+            tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+            tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+            tmem_ld_32x32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(sv[64]));
+            tmem_ld_32x32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(sv[96]));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[X]);                 // the score row is in registers: S_X may be overwritten by Q K^T(j+1)
+            if (r == 0) TA_DBG(X, 3);
+            float mx;
+            if (nvalid >= TA_BKV) {
+                // four independent max chains (the 128-long serial chain was ~640 cycles of exposed latency)
+                float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(t[i]));
-                } else {
+                for (int i = 4; i < 128; i += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(sv[i]));
+                    m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+                }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            } else {
+                mx = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(t[i]));
+                for (int i = 0; i < 128; ++i)
+                    if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            }
+            bool waited_o = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool need = (mx - m_ref) * scale_log2 > 8.0f;     // stale max tolerated up to 2^8
+                if (__any_sync(0xffffffffu, need)) {
+                    mbar_wait(&o_full[X], (j - 1) & 1);              // P V(j-1) retired: O_X is quiescent
+                    tc_fence_after();
+                    waited_o = true;
+                    const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
+                    if (need) { m_ref = mx; l_run *= a; }
+                    uint32_t t[32];
+                    tmem_ld_32x32(tO, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                    tmem_st_32x32(tO, t);
+                    tmem_ld_32x32(tO + 32, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                    tmem_st_32x32(tO + 32, t);
+                    tmem_ld_32x16(tO + 64, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                    tmem_st_32x16(tO + 64, t);
+                    tmem_st_wait();
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2((m_run - m_new) * scale_log2);
-            const float msc = m_new * scale_log2;
-            // ---- fold the previous tile's P V into the running output (its MMA ran while we waited for S) ----
-            if (j > 0) {
-                mbar_wait(&o_full[X], (j - 1) & 1);
-                tc_fence_after();
-                accumulate_o(alpha_prev);
-                tc_fence_before();
-                mbar_arrive(&o_free[X]);
-            }
-            alpha_prev = alpha;
-            // ---- pass 2: p = exp2(s*scale - m*scale) -> fp16 -> swizzled smem ; row sum ----
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t t[32];
-                tmem_ld_32x32(tS + c * 32, t);
-                tmem_ld_wait();
-                uint32_t pk[16];
-                if (nvalid >= (c + 1) * 32) {           // whole chunk valid: no masking instructions
+            const float msc = m_ref * scale_log2;
+            if (r == 0) TA_DBG(X, 4);
+            if (j > 0 && !waited_o) mbar_wait(&o_full[X], (j - 1) & 1);   // P_X buffer free (normally already true)
+            if (r == 0) TA_DBG(X, 5);
+            float rs0 = 0.f, rs1 = 0.f;
+            if (nvalid >= TA_BKV) {          // full tile: no masking instructions at all
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
-                        const float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
-                        rs += p0 + p1;
+                        const float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
+                        const float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
+                        rs0 += p0;
+                        rs1 += p1;
                         __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
-                } else {
+                    uint8_t* dst = pS + (c >> 1) * (128 * 128);
+                    const int cc0 = (c & 1) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        float p0 = ex2(fmaf(__uint_as_float(t[i]), scale_log2, -msc));
-                        float p1 = ex2(fmaf(__uint_as_float(t[i + 1]), scale_log2, -msc));
+                        float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
+                        float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
                         if (c * 32 + i >= nvalid) p0 = 0.f;
                         if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                        rs += p0 + p1;
+                        rs0 += p0;
+                        rs1 += p1;
                         __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
-                }
-                uint8_t* dst = pS + (c >> 1) * (128 * 128);
-                const int cc0 = (c & 1) * 4;
+                    uint8_t* dst = pS + (c >> 1) * (128 * 128);
+                    const int cc0 = (c & 1) * 4;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
             }
-            m_run = m_new;
-            l_run = l_run * alpha + rs;
-            tc_fence_before();
-            mbar_arrive(&s_free[X]);        // S_X drained: the next Q K^T may overwrite it
+            const float rs = rs0 + rs1;
+            l_run += rs;
+            if (r == 0) TA_DBG(X, 6);
             fence_proxy_async();            // make the P stores visible to the tensor core (async proxy)
+            tc_fence_before();
             mbar_arrive(&p_full[X]);
+            if (r == 0) TA_DBG(X, 7);
         }
         mbar_wait(&o_full[X], (nkt - 1) & 1);
         tc_fence_after();
-        accumulate_o(alpha_prev);
         const int row = q0 + X * TA_BQ + r;
-        if (row < Nq) {
-            const float inv = 1.0f / l_run;
-            __half* orow = out + (static_cast<size_t>(b) * Nq + row) * (H * Dh) + h * Dh;
+        const float inv = 1.0f / l_run;
+        __half* orow = out + (static_cast<size_t>(b) * Nq + (row < Nq ? row : 0)) * (H * Dh) + h * Dh;
 #pragma unroll
-            for (int d = 0; d < TA_DHP; d += 8) {
-                if (d < Dh) {
+        for (int c = 0; c < 3; ++c) {
+            uint32_t t[32];
+            if (c < 2) tmem_ld_32x32(tO + c * 32, t);
+            else tmem_ld_32x16(tO + 64, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d8 = 0; d8 < (c < 2 ? 32 : 16); d8 += 8) {
+                const int d = c * 32 + d8;
+                if (row < Nq && d < Dh) {
                     Pack8 v;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn(o[d + i] * inv);
+                    for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn(__uint_as_float(t[d8 + i]) * inv);
                     *reinterpret_cast<uint4*>(orow + d) = v.u;
                 }
             }
@@ -295,7 +378,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
 }  // namespace
 
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
-                        cudaStream_t st) {
+                        cudaStream_t st, long long* dbg) {
     TPX_CHECK(B > 0 && H > 0 && Nq > 0 && Nk > 0, TPX_ERR_SHAPE, "attention_tc: empty problem");
     TPX_CHECK(Dh % 8 == 0 && Dh <= TA_DHP && Dh > 64, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers 64 < Dh <= 80)", Dh);
     TPX_CHECK(NkPad % 8 == 0 && NkPad >= Nk, TPX_ERR_SHAPE, "attention_tc: NkPad %d must be a multiple of 8 and >= Nk %d", NkPad, Nk);
@@ -315,7 +398,7 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     }
     ProfScope prof(PROF_ATTENTION, st);
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f));
+    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

@@ -509,6 +509,12 @@ int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, in
                                Nq, Nk, NkPad, Dh, scale, static_cast<cudaStream_t>(stream));
 }
 
+int tpx_attention_tc_debug(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
+                            int64_t* timeline_dev, void* stream) {
+    return launch_attention_tc(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(vT), static_cast<__half*>(out), B, H,
+                               Nq, Nk, NkPad, Dh, scale, static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(timeline_dev));
+}
+
 int tpx_cfg_combine(const void* both, int64_t n_half, float s, void* out, void* stream) {
     TPX_CHECK(both != nullptr && out != nullptr, TPX_ERR_ARG, "cfg_combine: null argument");
     return launch_cfg_combine(static_cast<const __half*>(both), n_half, s, static_cast<__half*>(out), static_cast<cudaStream_t>(stream));

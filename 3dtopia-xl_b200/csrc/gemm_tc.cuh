@@ -297,13 +297,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_kb = g.num_kb;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // warp-converged producer: every lane follows the ring, one elected lane arms the barrier and issues the TMA
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if constexpr (AMODE == AMODE_LINEAR) {
@@ -318,37 +319,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // The whole warp runs this loop with warp-uniform control flow and one elected lane issues: descriptors and
+        // the TMEM address then live in uniform registers, which keeps the tcgen05.mma issue rate high.
+        constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_u + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_kmajor<Cfg::SW>(a_addr);
-                    const uint64_t bdesc = umma_desc_kmajor<Cfg::SW>(a_addr + Cfg::A_BYTES);
+                const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
+                const uint64_t adesc = umma_desc_kmajor<Cfg::SW>(a_addr);
+                const uint64_t bdesc = umma_desc_kmajor<Cfg::SW>(a_addr + Cfg::A_BYTES);
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         const int quad = warp & 3;

@@ -36,7 +36,7 @@ int launch_attention(const __half* q, const __half* k, const __half* v, __half* 
 
 // attention_tc.cu : tcgen05 version for 64 < Dh <= 80; vT is V transposed [B,H,80,NkPad]
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
-                        cudaStream_t st);
+                        cudaStream_t st, long long* dbg = nullptr);
 // gemm_tc.cu : cached 2-D TMA descriptor over a row-major fp16 matrix (swizzle = box_cols * 2 bytes: 128/64/32)
 int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out);
 

@@ -146,6 +146,10 @@ int tpx_ln_modulate(float* x, int rows, int D, float eps, const void* shift_f16,
 int tpx_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int Dh, int DhP, float scale, void* stream);
 /* Same contract on the tcgen05 path (64 < Dh <= 80): q,k [B,H,N,80]; vT = V transposed [B,H,80,NkPad], NkPad % 8 == 0. */
 int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale, void* stream);
+/* Same launch with a timeline probe: block 0 writes (tag, clock64) pairs of its MMA thread and of one softmax thread per
+ * query tile into timeline_dev (3 x 1024 int64, zero-initialised by the caller).  Tuning aid. */
+int tpx_attention_tc_debug(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
+                            int64_t* timeline_dev, void* stream);
 /* out = h(uncond + h(s * h(cond - uncond)))  over [cond; uncond] halves of n_half elements (dit_crossattn.py:210-213) */
 int tpx_cfg_combine(const void* both_f16, int64_t n_half, float s, void* out_f16, void* stream);
 /* GroupNorm(groups, eps, affine) [+ SiLU] on a channels-last fp16 volume [P, S3, C]  (vae3d_dib.py:109,112,131-139) */
