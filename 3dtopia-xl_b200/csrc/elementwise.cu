@@ -13,80 +13,68 @@ namespace tpx {
 // =====================================================================================================
 constexpr int LN_MAX_ITERS = 16;  // D <= 2048
 
-__global__ void __launch_bounds__(128) ln_modulate_kernel(float* __restrict__ x, int rows, int D, float eps, const __half* __restrict__ shift,
+template <int NI>   // NI = D / 128 float4 per lane: the row lives in exactly NI*4 registers
+__global__ void __launch_bounds__(256) ln_modulate_kernel(float* __restrict__ x, int rows, float eps, const __half* __restrict__ shift,
                                                           const __half* __restrict__ scale, int mod_bstride, int rows_per_batch, int mod_batches,
                                                           __half* __restrict__ out, const __half* __restrict__ pre_gate,
                                                           const __half* __restrict__ pre_const, int pre_row0) {
+    constexpr int D = NI * 128;
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    const int ni = D >> 7;
     const int bm = (row / rows_per_batch) % mod_batches;
-    float4 v[LN_MAX_ITERS];
+    float4 v[NI];
     float* xr = x + static_cast<size_t>(row) * D;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; ++i)
-        if (i < ni) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+    for (int i = 0; i < NI; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
     if (pre_gate != nullptr && row >= pre_row0) {
         const __half* gp = pre_gate + static_cast<size_t>(bm) * mod_bstride;
 #pragma unroll
-        for (int i = 0; i < LN_MAX_ITERS; ++i)
-            if (i < ni) {
-                const int c = (lane + 32 * i) * 4;
-                const __half2 g0 = *reinterpret_cast<const __half2*>(gp + c), g1 = *reinterpret_cast<const __half2*>(gp + c + 2);
-                const __half2 c0 = *reinterpret_cast<const __half2*>(pre_const + c), c1 = *reinterpret_cast<const __half2*>(pre_const + c + 2);
-                v[i].x += h2f_round(__low2float(g0) * __low2float(c0));
-                v[i].y += h2f_round(__high2float(g0) * __high2float(c0));
-                v[i].z += h2f_round(__low2float(g1) * __low2float(c1));
-                v[i].w += h2f_round(__high2float(g1) * __high2float(c1));
-                *reinterpret_cast<float4*>(xr + c) = v[i];
-            }
-    }
-    // shift / scale loads are issued before the reductions so their L2 latency overlaps the shuffles
-    const __half* shp = shift + static_cast<size_t>(bm) * mod_bstride;
-    const __half* scp = scale + static_cast<size_t>(bm) * mod_bstride;
-    uint2 shv[LN_MAX_ITERS], scv[LN_MAX_ITERS];
-#pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; ++i)
-        if (i < ni) {
+        for (int i = 0; i < NI; ++i) {
             const int c = (lane + 32 * i) * 4;
-            shv[i] = __ldg(reinterpret_cast<const uint2*>(shp + c));
-            scv[i] = __ldg(reinterpret_cast<const uint2*>(scp + c));
+            const __half2 g0 = *reinterpret_cast<const __half2*>(gp + c), g1 = *reinterpret_cast<const __half2*>(gp + c + 2);
+            const __half2 c0 = *reinterpret_cast<const __half2*>(pre_const + c), c1 = *reinterpret_cast<const __half2*>(pre_const + c + 2);
+            v[i].x += h2f_round(__low2float(g0) * __low2float(c0));
+            v[i].y += h2f_round(__high2float(g0) * __high2float(c0));
+            v[i].z += h2f_round(__low2float(g1) * __low2float(c1));
+            v[i].w += h2f_round(__high2float(g1) * __high2float(c1));
+            *reinterpret_cast<float4*>(xr + c) = v[i];
         }
+    }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; ++i)
-        if (i < ni) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) / D;
+    for (int i = 0; i < NI; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; ++i)
-        if (i < ni) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    for (int i = 0; i < NI; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const __half* shp = shift + static_cast<size_t>(bm) * mod_bstride;
+    const __half* scp = scale + static_cast<size_t>(bm) * mod_bstride;
     __half* orow = out + static_cast<size_t>(row) * D;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_ITERS; ++i)
-        if (i < ni) {
-            const int c = (lane + 32 * i) * 4;
-            const __half2 sh0 = *reinterpret_cast<const __half2*>(&shv[i].x), sh1 = *reinterpret_cast<const __half2*>(&shv[i].y);
-            const __half2 sc0 = *reinterpret_cast<const __half2*>(&scv[i].x), sc1 = *reinterpret_cast<const __half2*>(&scv[i].y);
-            const float m0 = h2f_round(1.0f + __low2float(sc0)), m1 = h2f_round(1.0f + __high2float(sc0));
-            const float m2 = h2f_round(1.0f + __low2float(sc1)), m3 = h2f_round(1.0f + __high2float(sc1));
-            const float y0 = (v[i].x - mean) * rstd * m0 + __low2float(sh0);
-            const float y1 = (v[i].y - mean) * rstd * m1 + __high2float(sh0);
-            const float y2 = (v[i].z - mean) * rstd * m2 + __low2float(sh1);
-            const float y3 = (v[i].w - mean) * rstd * m3 + __high2float(sh1);
-            __half2 o0 = __floats2half2_rn(y0, y1), o1 = __floats2half2_rn(y2, y3);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&o0);
-            pk.y = *reinterpret_cast<uint32_t*>(&o1);
-            *reinterpret_cast<uint2*>(orow + c) = pk;
-        }
+    for (int i = 0; i < NI; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const uint2 shv = __ldg(reinterpret_cast<const uint2*>(shp + c)), scv = __ldg(reinterpret_cast<const uint2*>(scp + c));
+        const __half2 sh0 = *reinterpret_cast<const __half2*>(&shv.x), sh1 = *reinterpret_cast<const __half2*>(&shv.y);
+        const __half2 sc0 = *reinterpret_cast<const __half2*>(&scv.x), sc1 = *reinterpret_cast<const __half2*>(&scv.y);
+        const float m0 = h2f_round(1.0f + __low2float(sc0)), m1 = h2f_round(1.0f + __high2float(sc0));
+        const float m2 = h2f_round(1.0f + __low2float(sc1)), m3 = h2f_round(1.0f + __high2float(sc1));
+        const float y0 = (v[i].x - mean) * rstd * m0 + __low2float(sh0);
+        const float y1 = (v[i].y - mean) * rstd * m1 + __high2float(sh0);
+        const float y2 = (v[i].z - mean) * rstd * m2 + __low2float(sh1);
+        const float y3 = (v[i].w - mean) * rstd * m3 + __high2float(sh1);
+        __half2 o0 = __floats2half2_rn(y0, y1), o1 = __floats2half2_rn(y2, y3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&o0);
+        pk.y = *reinterpret_cast<uint32_t*>(&o1);
+        *reinterpret_cast<uint2*>(orow + c) = pk;
+    }
 }
 
 int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift, const __half* scale, int mod_bstride, int rows_per_batch,
@@ -94,8 +82,17 @@ int launch_ln_modulate(float* x, int rows, int D, float eps, const __half* shift
     TPX_CHECK(D % 128 == 0 && D <= 128 * LN_MAX_ITERS, TPX_ERR_SHAPE, "ln_modulate: hidden size %d must be a multiple of 128 and <= %d", D, 128 * LN_MAX_ITERS);
     if (rows <= 0) return TPX_OK;
     ProfScope prof(PROF_LN, st);
-    TPX_CUDA(launch_pdl(ln_modulate_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, x, rows, D, eps, shift, scale, mod_bstride, rows_per_batch, mod_batches,
-                        out, pre_gate, pre_const, pre_row0));
+    const dim3 grid((rows + 7) / 8), block(256);
+#define TPX_LN_CASE(NI_)                                                                                                                         \
+    case NI_:                                                                                                                                    \
+        TPX_CUDA(launch_pdl(ln_modulate_kernel<NI_>, grid, block, 0, st, x, rows, eps, shift, scale, mod_bstride, rows_per_batch, mod_batches, out, \
+                            pre_gate, pre_const, pre_row0));                                                                                     \
+        break;
+    switch (D / 128) {
+        TPX_LN_CASE(1) TPX_LN_CASE(2) TPX_LN_CASE(3) TPX_LN_CASE(4) TPX_LN_CASE(5) TPX_LN_CASE(6) TPX_LN_CASE(7) TPX_LN_CASE(8)
+        TPX_LN_CASE(9) TPX_LN_CASE(10) TPX_LN_CASE(11) TPX_LN_CASE(12) TPX_LN_CASE(13) TPX_LN_CASE(14) TPX_LN_CASE(15) TPX_LN_CASE(16)
+    }
+#undef TPX_LN_CASE
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

@@ -119,27 +119,35 @@ class ClockSampler:
 
 
 # ---- reference arm / cpu baseline: the oracle port on the host cores -------------------------------------------------
-def cpu_oracle_steps_per_s(sample_blocks: int, reps: int):
+def cpu_oracle_steps_per_s(sample_blocks: int, reps: int, thread_options=None):
     """Times forward_with_cfg of the ORACLE (oracle/dit.py, fp32, the reference's CPU arithmetic) at full width on a
-    `sample_blocks`-deep stack and extrapolates linearly in depth to 28 blocks (blocks are identical in cost)."""
+    `sample_blocks`-deep stack and extrapolates linearly in depth to 28 blocks (blocks are identical in cost).
+    torch's CPU GEMMs do not always scale to every hardware thread, so a few thread counts are tried and the fastest
+    is reported together with the thread count it used."""
     import torch
     import oracle
     from tpxl_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
+    ncpu = os.cpu_count() or 1
+    if thread_options is None:
+        thread_options = sorted({ncpu, max(1, ncpu // 2), min(ncpu, 32)}, reverse=True)
     cfg = dict(synth.FULL_DIT, depth=sample_blocks)
     g = torch.Generator().manual_seed(0)
     sd = {k: torch.randn(s, generator=g) * 0.02 for k, s in synth.dit_shapes(**cfg).items()}
     x, y = torch.randn(1, N_TOK, CIN, generator=g), torch.randn(1, M_CTX, DC, generator=g)
     t = torch.tensor([960])
-    times = []
+    best = (float("inf"), ncpu)
     with torch.no_grad():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            oracle.dit.forward_with_cfg(sd, x, t, y, CFG_SCALE, H, "fp32")
-            times.append(time.perf_counter() - t0)
-    t_sample = min(times)
+        for nt in thread_options:
+            torch.set_num_threads(nt)
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                oracle.dit.forward_with_cfg(sd, x, t, y, CFG_SCALE, H, "fp32")
+                dt = time.perf_counter() - t0
+                if dt < best[0]:
+                    best = (dt, nt)
+    t_sample, cores = best
     t_step = t_sample * (L / sample_blocks)
-    return 1.0 / t_step, t_sample, torch.get_num_threads()
+    return 1.0 / t_step, t_sample, cores
 
 
 def run_reference(args):
@@ -148,8 +156,10 @@ def run_reference(args):
         return
     blocks = 2
     per = []
+    THREADS = None        # first step probes a few thread counts, later steps reuse the fastest
     for i in range(args.warmup + args.steps):
-        sps, t_sample, cores = cpu_oracle_steps_per_s(blocks, 1)
+        sps, t_sample, cores = cpu_oracle_steps_per_s(blocks, 1, thread_options=THREADS)
+        THREADS = [cores]
         if i >= args.warmup:
             per.append(sps)
     val = statistics.median(per)
@@ -339,9 +349,9 @@ def run_ours(args):
                               "frac": F_VAE / (vae_ms / 1e3) / 1e12 / peaks["bf16_tflops"], "peak": peaks["bf16_tflops"], "breakdown_ms": vae_cls}
     if not args.no_cpu and world >= 1:
         try:
-            sps, t_sample, cores = cpu_oracle_steps_per_s(2, 3)
+            sps, t_sample, cores = cpu_oracle_steps_per_s(2, 1)
             line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle forward_with_cfg fp32, 2-block stack at full width, best of 3 ({t_sample:.2f} s), extrapolated x14 to 28 blocks"}
+                                    "sample": f"oracle forward_with_cfg fp32, 2-block stack at full width, best over thread counts ({t_sample:.2f} s at {cores} threads), extrapolated x14 to 28 blocks"}
         except Exception as ex:  # never lose the GPU line over the CPU leg
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)

@@ -71,6 +71,9 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, pol: Policy) -> Tensor:
     """xformers memory_efficient_attention contract: q,k,v [B,N,H,Dh] -> [B,N,H,Dh]; scale Dh^-1/2."""
     scale = q.shape[-1] ** -0.5
     qh, kh, vh = (pol.rnd(a).permute(0, 2, 1, 3) for a in (q, k, v))
+    if not pol.amp and q.device.type == "cpu" and q.shape[1] * k.shape[1] > (1 << 20):
+        # same fp32 math through torch's fused CPU kernel (no [B,H,N,M] score tensor): keeps the CPU baseline honest
+        return F.scaled_dot_product_attention(qh, kh, vh, scale=scale).permute(0, 2, 1, 3)
     s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
     p = torch.softmax(s, dim=-1)
     o = torch.matmul(p, vh)
