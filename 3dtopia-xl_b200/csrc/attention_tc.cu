@@ -19,6 +19,8 @@
 //
 // Layouts: q, k  [B,H,N,80] fp16 (d >= 72 zero);  vT [B,H,80,NkPad] fp16 (V transposed: keys contiguous, NkPad % 8 == 0,
 // rows d >= 72 and key columns >= Nk finite/zero);  out [B,Nq,H*72] fp16.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace tpx {
@@ -80,9 +82,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                    int Dh, float scale_log2, long long* __restrict__ dbg) {
+                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_ns) {
     extern __shared__ uint8_t ta_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ta_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
+    // access to generic LD/ST instead of LDS/STS)
+    uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TA_OFF_BAR);
     uint64_t* q_full = bars;            // 1
     uint64_t* kv_full = bars + 1;       // TA_KV_STAGES
@@ -106,7 +110,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         mbar_init(q_full, 1);
         for (int i = 0; i < TA_KV_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
+            mbar_init(&kv_empty[i], 2);      // one commit from each of the two MMA issuer warps
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
@@ -157,8 +161,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // warp-converged issuer (uniform control flow, one elected lane issues): descriptors stay in uniform registers
+    } else if (warp == 1 || warp == 3) {
+        // Two warp-converged issuer warps (uniform control flow, one elected lane issues; descriptors stay in uniform
+        // registers): warp 1 drives query tile A, warp 3 tile B, so the two softmax warpgroups run as independent pipelines
+        // and can de-phase instead of being re-synchronised by one in-order issuer.
+        const int X = warp == 1 ? 0 : 1;
         constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
         constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
         const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
@@ -193,24 +200,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        issue_qk(0, 0);
-        issue_qk(1, 0);
+        issue_qk(X, 0);
         for (int j = 0; j < nkt; ++j) {
             const int s = j % TA_KV_STAGES;
-            if (j + 1 < nkt) {           // next scores first: both softmax warpgroups get S(j+1) while they exponentiate tile j
+            if (j + 1 < nkt) {           // next scores first: the warpgroup gets S(j+1) while it exponentiates tile j
                 const int sn = (j + 1) % TA_KV_STAGES;
                 mbar_wait(&kv_full[sn], ((j + 1) / TA_KV_STAGES) & 1);
-                for (int X = 0; X < 2; ++X) {
-                    mbar_wait(&s_free[X], j & 1);
-                    tc_fence_after();
-                    issue_qk(X, sn);
-                }
-            }
-            for (int X = 0; X < 2; ++X) {
-                mbar_wait(&p_full[X], j & 1);
+                mbar_wait(&s_free[X], j & 1);
                 tc_fence_after();
-                issue_pv(X, s, j > 0 ? 1u : 0u);      // O_X accumulates in TMEM across key tiles
+                issue_qk(X, sn);
             }
+            mbar_wait(&p_full[X], j & 1);
+            tc_fence_after();
+            issue_pv(X, s, j > 0 ? 1u : 0u);      // O_X accumulates in TMEM across key tiles
             if (elect_one()) umma_commit(&kv_empty[s]);
             __syncwarp();
         }
@@ -223,15 +225,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t tS = tmem_base + X * 128 + lane_off;
         const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
-        uint8_t* pS = smem + TA_OFF_P + X * TA_P_BYTES + r * 128;
+        const uint32_t pS = smem_u32(smem) + TA_OFF_P + X * TA_P_BYTES + r * 128;   // shared-window address of this row of P
         const int sw = r & 7;
         float m_ref = 0.f, l_run = 0.f;
+        // De-phase the two softmax warpgroups: they share the four MUFU units, so running their exponential phases in
+        // lockstep halves each one's rate while the XU idles during their (also simultaneous) load / max / sync phases.
         for (int j = 0; j < nkt; ++j) {
             const int nvalid = Nk - j * TA_BKV;      // keys of this tile that exist (>= 1)
             if (r == 0) TA_DBG(X, 1);
             mbar_wait(&s_full[X], j & 1);
             tc_fence_after();
             if (r == 0) TA_DBG(X, 2);
+            if (X == 1 && j == 0) __nanosleep(stagger_ns);   // after the first scores arrive, so the delay is not absorbed by the load wait
             uint32_t sv[128];
             tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
             tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
@@ -307,11 +312,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
-                    uint8_t* dst = pS + (c >> 1) * (128 * 128);
+                    const uint32_t dst = pS + (c >> 1) * (128 * 128);
                     const int cc0 = (c & 1) * 4;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((cc0 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                     : "memory");
                 }
             } else {
 #pragma unroll
@@ -328,11 +335,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
-                    uint8_t* dst = pS + (c >> 1) * (128 * 128);
+                    const uint32_t dst = pS + (c >> 1) * (128 * 128);
                     const int cc0 = (c & 1) * 4;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(dst + (((cc0 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((cc0 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                     : "memory");
                 }
             }
             const float rs = rs0 + rs1;
@@ -397,8 +406,9 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
+    static const unsigned stagger = getenv("TPX_ATT_STAGGER_NS") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER_NS"))) : 800u;
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg));
+    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }
