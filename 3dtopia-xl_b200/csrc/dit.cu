@@ -179,11 +179,35 @@ DitWs carve_ws(const tpx_dit* h, int S, uint8_t* base) {
     return w;
 }
 
+// tile width for the 2-CTA kernel (256-row pair tiles over gemm_num_sms()/2 clusters)
+int pick_bn_2cta(int M, int N) {
+    const int pairs = gemm_num_sms() / 2;
+    const int tm = (M + 255) / 256;
+    int best = 128;
+    long best_cost = -1;
+    for (int bn : {128, 192, 256}) {
+        const long tiles = static_cast<long>(tm) * ((N + bn - 1) / bn);
+        const long cost = ((tiles + pairs - 1) / pairs) * bn;
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best)) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+
+bool use_2cta() {
+    static const int v = getenv("TPX_GEMM_2CTA") ? atoi(getenv("TPX_GEMM_2CTA")) : 0;   // opt-in (TPX_GEMM_2CTA=1): see the note in gemm_tc2_kernel
+    return v != 0;
+}
+
+// tile_n: 0 = automatic; > 0 = 1-CTA kernel with that tile width; < 0 = 2-CTA (cta_group::2) kernel with width -tile_n
 int gemm_linear(const __half* A, int lda, const __half* W, int M, int N, int K, int epi, const GemmArgs& args, int tile_n, cudaStream_t st) {
     GemmProblem p{};
     p.A = A; p.a_mode = AMODE_LINEAR; p.lda = lda; p.W = W; p.M = M; p.N = N; p.K = K;
-    p.BN = tile_n > 0 ? tile_n : pick_bn(M, N);
     p.epi = epi; p.args = args;
+    if (tile_n < 0 || (tile_n == 0 && use_2cta() && M >= 256)) {
+        p.BN = tile_n < 0 ? -tile_n : pick_bn_2cta(M, N);
+        return launch_gemm_2cta(p, st);
+    }
+    p.BN = tile_n > 0 ? tile_n : pick_bn(M, N);
     return launch_gemm(p, st);
 }
 }  // namespace
@@ -353,7 +377,19 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     const int N = h->N, D = h->D, Ltot = h->Ltot, M = h->cond_M;
     const float qscale = 1.0f / sqrtf(static_cast<float>(h->Dh));
     int rc;
-#define TPX_RC(call) do { rc = (call); if (rc != TPX_OK) return rc; } while (0)
+    static const bool dbg_sync = getenv("TPX_DEBUG_SYNC") != nullptr && getenv("TPX_DEBUG_SYNC")[0] == '1';
+    int op_index = 0;
+#define TPX_RC(call)                                                                                              \
+    do {                                                                                                          \
+        rc = (call);                                                                                              \
+        if (rc != TPX_OK) return rc;                                                                              \
+        if (dbg_sync) {                                                                                           \
+            fprintf(stderr, "[tpx] op %d: %s\n", op_index, #call);                                               \
+            fflush(stderr);                                                                                       \
+            TPX_CUDA(cudaStreamSynchronize(st));                                                                  \
+        }                                                                                                         \
+        ++op_index;                                                                                               \
+    } while (0)
 
     // timestep embedding (fp32) -> silu -> fp16, then every adaLN modulation of the network in one GEMV pass
     TPX_RC(launch_gemv(GEMV_IN_TIMESTEP, GEMV_OUT_F32_SILU, h->Wt0, h->bt0, nullptr, reinterpret_cast<const long long*>(t), B, D, 256, w.th1, nullptr, D, st));

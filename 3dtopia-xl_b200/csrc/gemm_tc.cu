@@ -171,6 +171,46 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
     return TPX_OK;
 }
 
+template <int BN, int EPI>
+static int launch_one_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN>;
+    auto kern = gemm_tc2_kernel<BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((a.M + 255) / 256) * ((a.N + BN - 1) / BN);
+    const int pairs = gemm_num_sms() / 2;
+    const int clusters = tiles < pairs ? tiles : pairs;
+    kern<<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);   // plain launch (cluster dims compiled in); see the note in the kernel
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
+int launch_gemm_2cta(const GemmProblem& p, cudaStream_t stream) {
+    TPX_CHECK(p.a_mode == AMODE_LINEAR && p.M > 0 && p.N > 0 && p.K > 0, TPX_ERR_SHAPE, "gemm_2cta: linear problems only");
+    TPX_CHECK(p.N % 8 == 0 && p.K % 8 == 0, TPX_ERR_SHAPE, "gemm_2cta: N (%d) and K (%d) must be multiples of 8", p.N, p.K);
+    ProfScope prof(PROF_GEMM, stream);
+    GemmArgs a = p.args;
+    a.M = p.M;
+    a.N = p.N;
+    a.num_kb = (p.K + 63) / 64;
+    CUtensorMap ta, tb;
+    int rc = map_2d(p.A, p.M, p.K, p.lda, 128, 64, &ta);
+    if (rc != TPX_OK) return rc;
+    rc = map_2d(p.W, p.N, p.K, p.K, p.BN / 2, 64, &tb);
+    if (rc != TPX_OK) return rc;
+#define TPX_CASE2(BN_, EP_) \
+    if (p.BN == BN_ && p.epi == EP_) return launch_one_2cta<BN_, EP_>(ta, tb, a, stream);
+    TPX_CASE2(128, EPI_STORE) TPX_CASE2(128, EPI_GELU) TPX_CASE2(128, EPI_HEADS) TPX_CASE2(128, EPI_GATED)
+    TPX_CASE2(192, EPI_STORE) TPX_CASE2(192, EPI_GELU) TPX_CASE2(192, EPI_HEADS) TPX_CASE2(192, EPI_GATED)
+    TPX_CASE2(256, EPI_STORE) TPX_CASE2(256, EPI_GELU) TPX_CASE2(256, EPI_HEADS) TPX_CASE2(256, EPI_GATED)
+#undef TPX_CASE2
+    set_error("gemm_2cta: no kernel instantiated for BN=%d epi=%d", p.BN, p.epi);
+    return TPX_ERR_SHAPE;
+}
+
 int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     TPX_CHECK(p.M > 0 && p.N > 0 && p.K > 0, TPX_ERR_SHAPE, "gemm: empty problem %d x %d x %d", p.M, p.N, p.K);
     TPX_CHECK(p.N % 8 == 0 && p.K % 8 == 0, TPX_ERR_SHAPE, "gemm: N (%d) and K (%d) must be multiples of 8", p.N, p.K);

@@ -419,6 +419,227 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  CTA r owns rows
+// [m0 + 128 r, +128) (its own A tile, its own TMEM accumulator lanes) and loads HALF of the B tile (BN/2 rows of W);
+// the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), the hardware reads the two B halves from both
+// CTAs' shared memory.  Per SM this halves the B traffic from L2 and the B bytes written to shared memory per MMA cycle.
+//   full[stage]   lives in the LEADER: both CTAs' TMA loads complete_tx on it (peer bit masked off the mbarrier address)
+//   empty[stage]  one per CTA, released by a multicast tcgen05.commit from the leader
+//   tfull[acc]    one per CTA (multicast commit);  tempty[acc] in the leader, 256 arrivals (both CTAs' epilogue threads)
+// =====================================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address (-> even CTA of the pair)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on the same-offset barrier of BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BN>
+struct Gemm2Cfg {
+    static constexpr int BK = 64;
+    static constexpr int A_BYTES = 128 * BK * 2;
+    static constexpr int BH_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2048;
+    static_assert(BH_BYTES % 1024 == 0, "B half tile must stay 1024-B aligned");
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    using Cfg = Gemm2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int BK = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_gate = s_bias + 256;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);     // leader's producer arms it with the bytes of BOTH CTAs
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 256); // epilogue threads of both CTAs
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                     // barriers of both CTAs initialised before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // Launched WITHOUT programmatic dependent launch and without an early trigger: chains of PDL-overlapped cluster
+    // kernels hung intermittently on B200 (profiles/README.md, open issue), so this kernel is fully stream-serialised.
+    pdl_wait();   // no-op for a normally launched grid
+
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + 255) / 256;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = g.num_kb;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        const uint32_t full0 = smem_u32(&full_bar[0]) & kPeerBitMask;      // the leader's barriers, from either CTA
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_2sm(sa, &tmA, full0 + stage * 8, kb * BK, m_blk * 256 + static_cast<int>(rank) * 128);
+                    tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, full0 + stage * 8, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(256, BN);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_u + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_kmajor<128>(a_addr);
+                    const uint64_t bdesc = umma_desc_kmajor<128>(a_addr + Cfg::A_BYTES);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_2sm(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) umma_commit_2sm(&tfull_bar[acc]);
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quad = warp & 3;
+        const int et = threadIdx.x - 128;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool gate_in_smem = (EPI == EPI_GATED) && (g.rows_per_batch % 128 == 0);
+        const uint32_t tempty0 = smem_u32(&tempty_bar[0]) & kPeerBitMask;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            const int n0 = n_blk * BN;
+            const int row0 = m_blk * 256 + static_cast<int>(rank) * 128;
+            epi_bar_sync();
+            for (int c = et; c < BN; c += 128) {
+                const int col = n0 + c;
+                s_bias[c] = (g.bias != nullptr && col < g.N) ? __half2float(g.bias[col]) : 0.f;
+                if constexpr (EPI == EPI_GATED) {
+                    if (gate_in_smem) {
+                        const int b = (row0 / g.rows_per_batch) % g.gate_batches;
+                        s_gate[c] = col < g.N ? __half2float(g.gate[static_cast<size_t>(b) * g.gate_bstride + col]) : 0.f;
+                    }
+                }
+            }
+            epi_bar_sync();
+            const int row = row0 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            HeadCursor hc{0, 0, 0, 0, 0};
+            size_t head_row_off = 0;
+            if constexpr (EPI == EPI_HEADS) {
+                hc.which = n0 / g.split_cols;
+                const int c = n0 - hc.which * g.split_cols;
+                hc.head = c / g.Dh;
+                hc.d = c - hc.head * g.Dh;
+                hc.b = row / g.Nseq;
+                hc.n = row - hc.b * g.Nseq;
+                head_row_off = (static_cast<size_t>(hc.b) * g.H * g.Nseq + hc.n) * g.DhP;
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+                epi_chunk<EPI, 32>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty0 + acc * 8);     // leader's tempty, from both CTAs
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                     // neither CTA may exit (or free TMEM) while its peer can still signal / read it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 struct GemmProblem {
     // A operand
@@ -434,6 +655,7 @@ struct GemmProblem {
     GemmArgs args;      // epilogue fields (M,N,num_kb filled by the launcher)
 };
 int launch_gemm(const GemmProblem& p, cudaStream_t stream);
+int launch_gemm_2cta(const GemmProblem& p, cudaStream_t stream);   // cta_group::2 path (LINEAR, DiT epilogues, BN in {128,192,256})
 int gemm_num_sms();
 
 }  // namespace tpx

@@ -115,3 +115,31 @@ def test_error_paths():
         m.forward(torch.zeros(9, 128, 8, device=DEV), torch.zeros(9, dtype=torch.int64, device=DEV), torch.zeros(9, 4, 64, device=DEV))
     with pytest.raises(tpxl_b200._lib.TpxError):
         tpxl_b200.DiT(seq_length=8, in_channels=8, condition_channels=64, hidden_size=100, depth=1, num_heads=4).to(DEV)
+
+
+def test_full_model_full_size_against_oracle_and_batch_of_four():
+    """The shipped model end to end (28 blocks, 2048 tokens, 1370 context tokens): forward_with_cfg against the oracle
+    (fp16 policy and fp32) for one sample, then a batch of four samples (config #5: 4 samples per GPU -> 8 sequences per
+    forward) against the same samples run one at a time."""
+    sd = synth.device_state_dict(synth.dit_shapes(**synth.FULL_DIT), 81, DEV, torch.float16)
+    m = tpxl_b200.DiT(**synth.FULL_DIT)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(82)
+    x = torch.randn(4, 2048, 68, generator=g, device=DEV)
+    y = torch.randn(4, 1370, 768, generator=g, device=DEV)
+    t = torch.tensor([960, 960, 480, 40], device=DEV)
+    with torch.no_grad():
+        one = m.forward_with_cfg(x[:1], t[:1], y[:1].contiguous(), cfg_scale=6.0, enable_amp=True)
+        sdf = {k: v.float() for k, v in sd.items()}
+        o16 = oracle.dit.forward_with_cfg(sdf, x[:1], t[:1], y[:1], 6.0, 16, "fp16")
+        o32 = oracle.dit.forward_with_cfg(sdf, x[:1], t[:1], y[:1], 6.0, 16, "fp32")
+        del sdf
+        four = m.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True)
+        singles = torch.cat([m.forward_with_cfg(x[i:i + 1], t[i:i + 1], y[i:i + 1].contiguous(), cfg_scale=6.0, enable_amp=True) for i in range(4)])
+    r = dict(ours_vs_o16=rel_l2(one.float(), o16), ours_vs_o32=rel_l2(one.float(), o32), o16_vs_o32=rel_l2(o16, o32), batch_vs_single=rel_l2(four.float(), singles.float()))
+    print(r)
+    assert torch.isfinite(four.float()).all()
+    assert r["ours_vs_o16"] < 5e-3                      # 28 blocks deep, CFG 6: fp16 noise of both sides, amplified
+    assert r["ours_vs_o32"] < 2.5 * r["o16_vs_o32"] + 1e-4
+    assert r["batch_vs_single"] < 1e-3

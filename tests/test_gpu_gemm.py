@@ -84,3 +84,37 @@ def test_linear_heads_transposed_v():
     assert torch.all(vT[:, :, Dh:, :] == 0) and torch.all(k[..., Dh:] == 0)
     assert rel_l2(vT[:, :, :Dh, :], ref[:, :, 2].permute(0, 2, 3, 1)) < 2e-3
     assert rel_l2(q[..., :Dh], ref[:, :, 0].permute(0, 2, 1, 3)) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,tile", [(256, 128, 64, -128), (512, 256, 256, -256), (4096, 1152, 1152, -128), (4096, 3456, 1152, -192), (4096, 4608, 1152, -256),
+                                        (4096, 1152, 4608, -128), (2048, 1152, 1152, -128), (1370, 2304, 768, -256), (300, 136, 1152, -128)])
+def test_linear_two_cta_pairs(M, N, K, tile):
+    """cta_group::2 kernel (negative tile_n selects it): 256-row pair tiles, B split across the two CTAs of a cluster."""
+    A, W, b = _rand(M, K, seed=31), _rand(N, K, scale=K ** -0.5, seed=32), _rand(N, seed=33)
+    out = linear(A, W, b, tile_n=tile)
+    ref = linear_ref(A, W, b)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 2e-3, (M, N, K, tile)
+    assert rel_l2(linear(A, W, b, act=1, tile_n=tile), linear_ref(A, W, b, act=1)) < 2e-3
+
+
+def test_two_cta_gated_and_heads_epilogues():
+    B, N, H, Dh, DhP, K = 2, 512, 16, 72, 80, 256
+    D = H * Dh
+    A, W, b = _rand(B * N, K, seed=41), _rand(3 * D, K, scale=1 / 16, seed=42), _rand(3 * D, seed=43)
+    q = torch.zeros(B, H, N, DhP, dtype=torch.float16, device="cuda")
+    k = torch.zeros_like(q)
+    vT = torch.zeros(B, H, DhP, N, dtype=torch.float16, device="cuda")
+    _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), q.data_ptr(), k.data_ptr(), vT.data_ptr(),
+                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, -192, 2, N, st()))
+    ref = linear_ref(A, W, b).reshape(B, N, 3, H, Dh)
+    torch.cuda.synchronize()
+    assert rel_l2(q[..., :Dh], ref[:, :, 0].permute(0, 2, 1, 3)) < 2e-3 and rel_l2(vT[:, :, :Dh, :], ref[:, :, 2].permute(0, 2, 3, 1)) < 2e-3
+    Wp, bp = _rand(D, K, scale=1 / 16, seed=44), _rand(D, seed=45)
+    gate = _rand(1, D, seed=46)
+    x = torch.randn(B * N, D, device="cuda")
+    x0 = x.clone()
+    _lib.check(_lib.lib().tpx_linear_gated(A.data_ptr(), K, Wp.data_ptr(), bp.data_ptr(), gate.data_ptr(), D, 1, N, x.data_ptr(), D, B * N, D, K, -128, st()))
+    refx = x0 + (gate[0].float() * linear_ref(A, Wp, bp).float()).half().float()
+    torch.cuda.synchronize()
+    assert rel_l2(x, refx) < 1e-3

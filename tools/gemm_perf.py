@@ -19,7 +19,7 @@ def main():
     lib = _lib.lib()
     for (M, N, K) in [(4096, 1152, 1152), (4096, 3456, 1152), (4096, 4608, 1152), (4096, 1152, 4608), (2048, 1152, 1152)]:
         A = torch.randn(M, K, device="cuda").half(); W = torch.randn(N, K, device="cuda").half() * K ** -0.5; b = torch.randn(N, device="cuda").half()
-        for tile in (128, 192, 256):
+        for tile in (128, 192, 256, -128, -192, -256):
             for act in (0, 1):
                 ms = timeit(lambda: linear(A, W, b, act=act, tile_n=tile))
                 print(f"linear M={M} N={N} K={K} tile={tile} act={act}: {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s", flush=True)
