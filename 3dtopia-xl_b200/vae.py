@@ -103,7 +103,7 @@ class VAE(nn.Module):
                 _lib.load_library().tpx_vae_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            self.__dict__["_handle"] = None      # not nn.Module.__setattr__: this also runs at interpreter shutdown
 
     def __del__(self):
         self._destroy_handle()

@@ -154,7 +154,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    blocks = 2
+    blocks = 2            # two blocks per step: ~5 s per sample on the GPU box's host, so a 25-step run stays within a few minutes
     per = []
     THREADS = None        # first step probes a few thread counts, later steps reuse the fastest
     for i in range(args.warmup + args.steps):
