@@ -9,9 +9,10 @@ import types
 
 from . import synth  # noqa: F401
 from . import _lib  # noqa: F401
-from . import diffusion, dit, vae  # noqa: F401
+from . import diffusion, dit, primsdf, vae  # noqa: F401
 from .diffusion import SpacedDiffusion, create_diffusion  # noqa: F401
 from .dit import DiT  # noqa: F401
+from .primsdf import PrimSDF  # noqa: F401
 from .vae import VAE  # noqa: F401
 
 __version__ = "0.1.0"
@@ -19,7 +20,8 @@ __version__ = "0.1.0"
 
 def install() -> None:
     """Make the reference's import paths resolve to this implementation, so ``inference.py`` / ``app.py`` run
-    unchanged:  ``models.dit_crossattn`` -> dit, ``models.vae3d_dib`` -> vae, ``models.diffusion`` -> diffusion.
+    unchanged:  ``models.dit_crossattn`` -> dit, ``models.vae3d_dib`` -> vae, ``models.diffusion`` -> diffusion,
+    ``models.primsdf`` -> primsdf.
     (Equivalent to editing ``class_name`` in configs/inference_dit.yml:32,53; see INTEGRATION.md.)  If the reference's
     ``models`` package is importable it is imported first so its other members (conditioner, primsdf) keep working."""
     try:
@@ -28,6 +30,6 @@ def install() -> None:
         ref_models = types.ModuleType("models")
         ref_models.__path__ = []
         sys.modules["models"] = ref_models
-    for name, mod in (("dit_crossattn", dit), ("vae3d_dib", vae), ("diffusion", diffusion)):
+    for name, mod in (("dit_crossattn", dit), ("vae3d_dib", vae), ("diffusion", diffusion), ("primsdf", primsdf)):
         sys.modules["models." + name] = mod
         setattr(ref_models, name, mod)

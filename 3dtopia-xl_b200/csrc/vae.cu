@@ -319,6 +319,12 @@ int tpx_vae_decode(tpx_vae* h, const void* z, int z_dtype, void* out, int out_dt
     return TPX_OK;
 }
 
+int tpx_primsdf_query(const float* x, const float* srt, const float* feat, int64_t n, int K, int S, int dim_feat, int inference, float* out, void* stream) {
+    if (n == 0) return TPX_OK;
+    TPX_CHECK(n > 0 && x != nullptr && srt != nullptr && feat != nullptr && out != nullptr, TPX_ERR_ARG, "primsdf_query: null argument or negative n");
+    return launch_primsdf_query(x, srt, feat, n, K, S, dim_feat, inference, out, static_cast<cudaStream_t>(stream));
+}
+
 int tpx_groupnorm_silu(const void* x, const void* gamma, const void* beta, int P, int S3, int C, int groups, float eps, int apply_silu, void* out,
                        void* stream) {
     TPX_CHECK(x != nullptr && gamma != nullptr && beta != nullptr && out != nullptr, TPX_ERR_ARG, "groupnorm_silu: null argument");

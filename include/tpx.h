@@ -160,6 +160,16 @@ int tpx_groupnorm_silu(const void* x_f16, const void* gamma_f16, const void* bet
 int tpx_conv3d_k3(const void* x_f16, const void* W_f16, const void* bias_f16, const void* resid_f16, float alpha, void* out_f16, int P, int S, int C,
                   int Cout, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * PrimSDF point query — models/primsdf.py:52-109 (PrimSDF.forward = prim_weight + grid_sample_feat), the consumer of
+ * the decoded voxels.  x device fp32 [n,3]; srt device fp32 [K,4] = (scale, tx, ty, tz), 16-B aligned;
+ * feat device fp32 [K, dim_feat*S^3] channel-major (inference.py:347); out device fp32 [n, dim_feat]:
+ * column 0 = sdf, 1..3 = rgb clipped to [0,1], 4..5 = roughness/metallic clipped.  inference != 0 applies the
+ * nearest-voxel SDF approximation to points no primitive covers (primsdf.py:82-101).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tpx_primsdf_query(const float* x_dev, const float* srt_dev, const float* feat_dev, int64_t n, int K, int S, int dim_feat, int inference,
+                      float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,6 +152,23 @@ def main():
                         stage_up1_slice=stages["up1"][0, :, 3, 4, :].numpy(), stage_mid_slice=stages["mid"][1, :8].numpy())
     print("vae", tuple(out.shape), float(out.abs().mean()))
 
+    # ---- PrimSDF point query: the reference class, with `trimesh` (imported but unused on this path) stubbed
+    sys.modules.setdefault("trimesh", types.ModuleType("trimesh"))
+    from models.primsdf import PrimSDF              # noqa: E402
+    rs = np.random.RandomState(1104)
+    K, S = 96, 8
+    srt = np.concatenate([rs.uniform(0.05, 0.25, size=(K, 1)), rs.uniform(-0.8, 0.8, size=(K, 3))], axis=1).astype(np.float32)
+    feat = rs.standard_normal(size=(K, 6 * S ** 3)).astype(np.float32)
+    pts = rs.uniform(-1, 1, size=(4000, 3)).astype(np.float32)
+    m = PrimSDF(num_prims=K, dim_feat=6, prim_shape=S).eval()
+    m.srt_param.data = torch.from_numpy(srt)
+    m.feat_param.data = torch.from_numpy(feat)
+    preds = m(torch.from_numpy(pts))
+    covered = (m.prim_weight(torch.from_numpy(pts)).sum(1) > 0).numpy()
+    np.savez_compressed(os.path.join(OUT, "primsdf.npz"), srt=srt, feat=feat, pts=pts, covered=covered,
+                        sdf=preds["sdf"].numpy(), tex=preds["tex"].numpy(), mat=preds["mat"].numpy())
+    print("primsdf", int(covered.sum()), "of", len(pts), "points covered")
+
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Time the PrimSDF point query at the reference's mesh-extraction size: 256^3 grid points against 2048 primitives
+(inference.py:108-116 walks them in 8192-point chunks through a dense weight matrix).  Prints ms and points/s; also times
+the oracle's dense torch formulation on the GPU for a 64-chunk sample as the stock-code comparison."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402  (comparison leg only)
+import tpxl_b200  # noqa: E402
+
+
+def main():
+    K, S, G = 2048, 8, int(os.environ.get("GRID", 256))
+    g = torch.Generator().manual_seed(0)
+    # a plausible object: primitives on a noisy sphere shell, scales ~ what the released VAE emits
+    d = torch.randn(K, 3, generator=g)
+    pos = d / d.norm(dim=1, keepdim=True) * (0.55 + 0.1 * torch.rand(K, 1, generator=g))
+    srt = torch.cat([0.03 + 0.05 * torch.rand(K, 1, generator=g), pos], 1)
+    m = tpxl_b200.PrimSDF(num_prims=K, dim_feat=6, prim_shape=S).eval()
+    m.srt_param.data = srt
+    m.feat_param.data = torch.randn(K, 6 * S ** 3, generator=g)
+    m = m.cuda()
+    lin = torch.linspace(-1, 1, G, device="cuda")
+    pts = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(-1, 3).contiguous()
+    for _ in range(2):
+        out = m(pts)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        out = m(pts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    cov = float((out["tex"].sum(1) != 0).float().mean())
+    print(f"tpx_primsdf_query: {pts.shape[0]} points x {K} prims  {ms:.2f} ms  {pts.shape[0] / ms / 1e6:.2f} Gpoints/s  "
+          f"({pts.shape[0] * K / ms / 1e9:.2f} T box-tests/s)  covered {cov:.3f}")
+    # stock formulation (dense weight matrix per 8192-point chunk) on the same GPU, 64 chunks
+    srt_d, feat_d = m.srt_param.data, m.feat_param.data
+    chunks = pts[: 64 * 8192].split(8192)
+    oracle.primsdf.query(chunks[0], srt_d, feat_d)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for c in chunks:
+        oracle.primsdf.query(c, srt_d, feat_d)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) * 1e3
+    print(f"dense torch formulation on GPU: {dt / 64:.3f} ms per 8192-point chunk -> {dt / 64 * pts.shape[0] / 8192:.0f} ms for the grid")
+
+
+if __name__ == "__main__":
+    main()
