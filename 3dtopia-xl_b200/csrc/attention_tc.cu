@@ -83,7 +83,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_ns) {
+                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_ns, int stale_max) {
     extern __shared__ uint8_t ta_smem_raw[];
     // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
     // access to generic LD/ST instead of LDS/STS)
@@ -219,7 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int X = (warp - 4) >> 2;               // query tile of this warpgroup
         const int quad = warp & 3;
         const int r = quad * 32 + lane;              // row in the tile == TMEM lane
@@ -247,71 +247,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             tc_fence_before();
             mbar_arrive(&s_free[X]);                 // the score row is in registers: S_X may be overwritten by Q K^T(j+1)
             if (r == 0) TA_DBG(X, 3);
-            float mx;
-            if (nvalid >= TA_BKV) {
-                // four independent max chains (the 128-long serial chain was ~640 cycles of exposed latency)
-                float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+            // O_X rescale by 2^((m_ref - mx) * scale) for the rows whose running maximum grew past the lazy threshold
+            auto rescale_o = [&](bool need, float mx) {
+                const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
+                if (need) { m_ref = mx; l_run *= a; }
+                uint32_t t[32];
+                tmem_ld_32x32(tO, t);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 4; i < 128; i += 4) {
-                    m0 = fmaxf(m0, __uint_as_float(sv[i]));
-                    m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
-                    m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
-                    m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
-                }
-                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            } else {
-                mx = -INFINITY;
+                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                tmem_st_32x32(tO, t);
+                tmem_ld_32x32(tO + 32, t);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
-            }
-            bool waited_o = false;
-            if (j == 0) {
-                m_ref = mx;
-            } else {
-                const bool need = (mx - m_ref) * scale_log2 > 8.0f;     // stale max tolerated up to 2^8
-                if (__any_sync(0xffffffffu, need)) {
-                    mbar_wait(&o_full[X], (j - 1) & 1);              // P V(j-1) retired: O_X is quiescent
-                    tc_fence_after();
-                    waited_o = true;
-                    const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
-                    if (need) { m_ref = mx; l_run *= a; }
-                    uint32_t t[32];
-                    tmem_ld_32x32(tO, t);
-                    tmem_ld_wait();
+                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                tmem_st_32x32(tO + 32, t);
+                tmem_ld_32x16(tO + 64, t);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-                    tmem_st_32x32(tO, t);
-                    tmem_ld_32x32(tO + 32, t);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-                    tmem_st_32x32(tO + 32, t);
-                    tmem_ld_32x16(tO + 64, t);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-                    tmem_st_32x16(tO + 64, t);
-                    tmem_st_wait();
-                }
-            }
-            const float msc = m_ref * scale_log2;
-            if (r == 0) TA_DBG(X, 4);
-            if (j > 0 && !waited_o) mbar_wait(&o_full[X], (j - 1) & 1);   // P_X buffer free (normally already true)
-            if (r == 0) TA_DBG(X, 5);
+                for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+                tmem_st_32x16(tO + 64, t);
+                tmem_st_wait();
+            };
             float rs0 = 0.f, rs1 = 0.f;
-            if (nvalid >= TA_BKV) {          // full tile: no masking instructions at all
+            if (j > 0 && nvalid >= TA_BKV && stale_max) {
+                // Fast path (every full tile after the first).  The lazy-rescale rule already tolerates a reference maximum that
+                // is stale by up to 2^8, so the exponentials do not have to wait for this tile's row maximum: they run against
+                // m_ref while the maximum is reduced in the same instruction stream (its ~600-cycle dependent chain hides
+                // under the MUFU-bound exponentials).  Only if some row's maximum did jump past the threshold is the tile redone.
+                mbar_wait(&o_full[X], (j - 1) & 1);              // P V(j-1) retired: P_X may be rewritten, O_X is quiescent
+                tc_fence_after();
+                if (r == 0) TA_DBG(X, 5);
+                const float msc = m_ref * scale_log2;
+                float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
-                        const float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
-                        rs0 += p0;
-                        rs1 += p1;
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float s0 = __uint_as_float(sv[c * 32 + i]), s1 = __uint_as_float(sv[c * 32 + i + 1]);
+                        const float s2 = __uint_as_float(sv[c * 32 + i + 2]), s3 = __uint_as_float(sv[c * 32 + i + 3]);
+                        m0 = fmaxf(m0, fmaxf(s0, s2)); m1 = fmaxf(m1, fmaxf(s1, s3));      // 3-input FMNMX3, two chains
+                        const float p0 = ex2(fmaf(s0, scale_log2, -msc)), p1 = ex2(fmaf(s1, scale_log2, -msc));
+                        const float p2 = ex2(fmaf(s2, scale_log2, -msc)), p3 = ex2(fmaf(s3, scale_log2, -msc));
+                        rs0 += p0 + p2;
+                        rs1 += p1 + p3;
+                        __half2 ha = __floats2half2_rn(p0, p1), hb = __floats2half2_rn(p2, p3);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&ha);
+                        pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hb);
                     }
                     const uint32_t dst = pS + (c >> 1) * (128 * 128);
                     const int cc0 = (c & 1) * 4;
@@ -321,7 +304,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                                      "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                                      : "memory");
                 }
+                const float mx = fmaxf(m0, m1);
+                const bool need = (mx - m_ref) * scale_log2 > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {             // rare: redo this tile against the new maximum
+                    rescale_o(need, mx);
+                    const float msc2 = m_ref * scale_log2;
+                    rs0 = 0.f; rs1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc2));
+                            const float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc2));
+                            rs0 += p0;
+                            rs1 += p1;
+                            __half2 hh = __floats2half2_rn(p0, p1);
+                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                        const uint32_t dst = pS + (c >> 1) * (128 * 128);
+                        const int cc0 = (c & 1) * 4;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((cc0 + q) ^ sw) << 4)), "r"(pk[4 * q]),
+                                         "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                         : "memory");
+                    }
+                }
             } else {
+                // First tile, ragged last tile (or stale_max off): maximum first, then the exponentials.
+                float mx = -INFINITY;
+                if (nvalid >= TA_BKV) {
+                    float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+                    for (int i = 4; i < 128; i += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(sv[i]));
+                        m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+                    }
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i)
+                        if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                }
+                bool waited_o = false;
+                if (j == 0) {
+                    m_ref = mx;
+                } else {
+                    const bool need = (mx - m_ref) * scale_log2 > 8.0f;     // stale max tolerated up to 2^8
+                    if (__any_sync(0xffffffffu, need)) {
+                        mbar_wait(&o_full[X], (j - 1) & 1);              // P V(j-1) retired: O_X is quiescent
+                        tc_fence_after();
+                        waited_o = true;
+                        rescale_o(need, mx);
+                    }
+                }
+                const float msc = m_ref * scale_log2;
+                if (r == 0) TA_DBG(X, 4);
+                if (j > 0 && !waited_o) mbar_wait(&o_full[X], (j - 1) & 1);   // P_X buffer free (normally already true)
+                if (r == 0) TA_DBG(X, 5);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
@@ -408,8 +451,10 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     }
     ProfScope prof(PROF_ATTENTION, st);
     static const unsigned stagger = getenv("TPX_ATT_STAGGER_NS") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER_NS"))) : 800u;
+    static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger));
+    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
+                        stale_max));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }
