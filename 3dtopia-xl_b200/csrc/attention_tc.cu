@@ -29,6 +29,7 @@ namespace tpx {
 namespace {
 
 constexpr int TA_DHP = 80;
+constexpr int TA_SUMROW = 72;                           // = Dh: the first padding row of V^T / column of O carries the softmax row sums
 constexpr int TA_BQ = 128, TA_BKV = 128;
 constexpr int TA_Q_BYTES = 128 * 128 + 128 * 32;        // 64-wide SW128 part + 16-wide SW32 part
 constexpr int TA_K_BYTES = TA_Q_BYTES;
@@ -49,6 +50,19 @@ __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x on the FMA pipe: x = n + r with n = round(x), r in [-0.5, 0.5]; cubic minimax for 2^r (max relative error 7.5e-5, below
+// the fp16 rounding P gets anyway); n goes straight into the exponent field.  Takes a share of the exponentials off the
+// MUFU unit, which is the bound of the softmax warps (16 ex2/clk/SM: 2048 cycles per 2x128x128 tile pair).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float fl = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold n
+    const float r = x - (fl - 12582912.0f);
+    float p = fmaf(0.0551716648f, r, 0.2426111251f);
+    p = fmaf(p, r, 0.6932609677f);
+    p = fmaf(p, r, 0.9999280572f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(fl) << 23));
 }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -80,6 +94,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
         }                                                                                    \
     } while (0)
 
+// POLY: every POLY-th exponential of a full tile is evaluated by ex2_poly instead of MUFU.EX2 (0 = none).
+template <int POLY>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
@@ -198,8 +214,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             }
             __syncwarp();
         };
+        // Row sums on the tensor core: row Dh of every V^T tile (a padding row, Dh < 80) is overwritten with ones after the TMA
+        // lands, so column Dh of O accumulates sum_k P[r,k] — rescaled together with O — and the softmax threads carry no sum.
+        // Both issuer warps write the same 2 x 128 bytes (row 72 is swizzle row 0: identity chunk order).
+        auto write_ones = [&](int s) {
+            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + TA_SUMROW * 128 + lane * 4;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + TA_VBOX_BYTES), "r"(0x3C003C00u) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+        };
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
+        write_ones(0);
         tc_fence_after();
         issue_qk(X, 0);
         for (int j = 0; j < nkt; ++j) {
@@ -207,6 +234,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             if (j + 1 < nkt) {           // next scores first: the warpgroup gets S(j+1) while it exponentiates tile j
                 const int sn = (j + 1) % TA_KV_STAGES;
                 mbar_wait(&kv_full[sn], ((j + 1) / TA_KV_STAGES) & 1);
+                write_ones(sn);
                 mbar_wait(&s_free[X], j & 1);
                 tc_fence_after();
                 issue_qk(X, sn);
@@ -228,7 +256,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
         const uint32_t pS = smem_u32(smem) + TA_OFF_P + X * TA_P_BYTES + r * 128;   // shared-window address of this row of P
         const int sw = r & 7;
-        float m_ref = 0.f, l_run = 0.f;
+        float m_ref = 0.f;
         // De-phase the two softmax warpgroups: they share the four MUFU units, so running their exponential phases in
         // lockstep halves each one's rate while the XU idles during their (also simultaneous) load / max / sync phases.
         for (int j = 0; j < nkt; ++j) {
@@ -250,7 +278,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             // O_X rescale by 2^((m_ref - mx) * scale) for the rows whose running maximum grew past the lazy threshold
             auto rescale_o = [&](bool need, float mx) {
                 const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
-                if (need) { m_ref = mx; l_run *= a; }
+                if (need) m_ref = mx;
                 uint32_t t[32];
                 tmem_ld_32x32(tO, t);
                 tmem_ld_wait();
@@ -269,7 +297,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 tmem_st_32x16(tO + 64, t);
                 tmem_st_wait();
             };
-            float rs0 = 0.f, rs1 = 0.f;
             if (j > 0 && nvalid >= TA_BKV && stale_max) {
                 // Fast path (every full tile after the first).  The lazy-rescale rule already tolerates a reference maximum that
                 // is stale by up to 2^8, so the exponentials do not have to wait for this tile's row maximum: they run against
@@ -288,10 +315,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         const float s0 = __uint_as_float(sv[c * 32 + i]), s1 = __uint_as_float(sv[c * 32 + i + 1]);
                         const float s2 = __uint_as_float(sv[c * 32 + i + 2]), s3 = __uint_as_float(sv[c * 32 + i + 3]);
                         m0 = fmaxf(m0, fmaxf(s0, s2)); m1 = fmaxf(m1, fmaxf(s1, s3));      // 3-input FMNMX3, two chains
-                        const float p0 = ex2(fmaf(s0, scale_log2, -msc)), p1 = ex2(fmaf(s1, scale_log2, -msc));
-                        const float p2 = ex2(fmaf(s2, scale_log2, -msc)), p3 = ex2(fmaf(s3, scale_log2, -msc));
-                        rs0 += p0 + p2;
-                        rs1 += p1 + p3;
+                        // element (i + k) of the row goes to the FMA-pipe polynomial when its index is a multiple of POLY
+                        const float p0 = (POLY > 0 && (c * 32 + i) % POLY == 0) ? ex2_poly(fmaf(s0, scale_log2, -msc)) : ex2(fmaf(s0, scale_log2, -msc));
+                        const float p1 = (POLY > 0 && (c * 32 + i + 1) % POLY == 0) ? ex2_poly(fmaf(s1, scale_log2, -msc)) : ex2(fmaf(s1, scale_log2, -msc));
+                        const float p2 = (POLY > 0 && (c * 32 + i + 2) % POLY == 0) ? ex2_poly(fmaf(s2, scale_log2, -msc)) : ex2(fmaf(s2, scale_log2, -msc));
+                        const float p3 = (POLY > 0 && (c * 32 + i + 3) % POLY == 0) ? ex2_poly(fmaf(s3, scale_log2, -msc)) : ex2(fmaf(s3, scale_log2, -msc));
                         __half2 ha = __floats2half2_rn(p0, p1), hb = __floats2half2_rn(p2, p3);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&ha);
                         pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hb);
@@ -309,7 +337,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 if (__any_sync(0xffffffffu, need)) {             // rare: redo this tile against the new maximum
                     rescale_o(need, mx);
                     const float msc2 = m_ref * scale_log2;
-                    rs0 = 0.f; rs1 = 0.f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t pk[16];
@@ -317,8 +344,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         for (int i = 0; i < 32; i += 2) {
                             const float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc2));
                             const float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc2));
-                            rs0 += p0;
-                            rs1 += p1;
                             __half2 hh = __floats2half2_rn(p0, p1);
                             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                         }
@@ -374,8 +399,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
                         if (c * 32 + i >= nvalid) p0 = 0.f;
                         if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                        rs0 += p0;
-                        rs1 += p1;
                         __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                     }
@@ -388,8 +411,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                                      : "memory");
                 }
             }
-            const float rs = rs0 + rs1;
-            l_run += rs;
             if (r == 0) TA_DBG(X, 6);
             fence_proxy_async();            // make the P stores visible to the tensor core (async proxy)
             tc_fence_before();
@@ -399,14 +420,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         mbar_wait(&o_full[X], (nkt - 1) & 1);
         tc_fence_after();
         const int row = q0 + X * TA_BQ + r;
-        const float inv = 1.0f / l_run;
         __half* orow = out + (static_cast<size_t>(b) * Nq + (row < Nq ? row : 0)) * (H * Dh) + h * Dh;
+        uint32_t t2[32];
+        tmem_ld_32x16(tO + 64, t2);                  // columns 64..79: the last 8 value columns and, at column Dh, the row sum
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(t2[TA_SUMROW - 64]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t t[32];
-            if (c < 2) tmem_ld_32x32(tO + c * 32, t);
-            else tmem_ld_32x16(tO + 64, t);
-            tmem_ld_wait();
+            if (c < 2) {
+                tmem_ld_32x32(tO + c * 32, t);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = t2[i];
+            }
 #pragma unroll
             for (int d8 = 0; d8 < (c < 2 ? 32 : 16); d8 += 8) {
                 const int d = c * 32 + d8;
@@ -433,7 +461,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
                         cudaStream_t st, long long* dbg) {
     TPX_CHECK(B > 0 && H > 0 && Nq > 0 && Nk > 0, TPX_ERR_SHAPE, "attention_tc: empty problem");
-    TPX_CHECK(Dh % 8 == 0 && Dh <= TA_DHP && Dh > 64, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers 64 < Dh <= 80)", Dh);
+    TPX_CHECK(Dh == TA_SUMROW, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers Dh = 72: 80-wide tiles whose first padding row carries the row sums)", Dh);
     TPX_CHECK(NkPad % 8 == 0 && NkPad >= Nk, TPX_ERR_SHAPE, "attention_tc: NkPad %d must be a multiple of 8 and >= Nk %d", NkPad, Nk);
     TPX_CHECK(H <= 65535 && B <= 65535, TPX_ERR_SHAPE, "attention_tc: grid too large");
     CUtensorMap mQa, mQb, mKa, mKb, mV;
@@ -444,16 +472,20 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 64, &mKa)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 16, &mKb)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(vT, static_cast<long long>(B) * H * TA_DHP, NkPad, NkPad, TA_DHP, 64, &mV)) != TPX_OK) return rc;
+    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 4;   // every poly-th exponential on the FMA pipe (0, 3 or 4)
+    auto kern = poly == 0 ? attention_tc_kernel<0> : (poly == 3 ? attention_tc_kernel<3> : attention_tc_kernel<4>);
     static bool attr_set = false;
     if (!attr_set) {
-        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
     static const unsigned stagger = getenv("TPX_ATT_STAGGER_NS") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER_NS"))) : 800u;
     static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    TPX_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
+    TPX_CUDA(launch_pdl(kern, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
                         stale_max));
     TPX_LAUNCH_CHECK();
     return TPX_OK;

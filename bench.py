@@ -350,7 +350,7 @@ def run_ours(args):
                      "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
                      "flops_per_step": fx["gemm"], "launches_per_step": n_cls[0], "ms_per_step": gemm_ms,
                      "share_of_step": gemm_ms / step_ms_prof if step_ms_prof else None},
-        "attention": {"kernel": "attention_kernel<80> (mma.sync flash attention)", "achieved": attn_tf, "unit": "TFLOP/s", "frac": attn_tf / peak_tf if peak_tf else None,
+        "attention": {"kernel": "attention_tc_kernel (tcgen05 flash attention, S/O in TMEM)", "achieved": attn_tf, "unit": "TFLOP/s", "frac": attn_tf / peak_tf if peak_tf else None,
                       "ms_per_step": ms_cls[1], "launches_per_step": n_cls[1], "share_of_step": ms_cls[1] / step_ms_prof if step_ms_prof else None},
         "step_breakdown_ms": {"gemm": ms_cls[0], "attention": ms_cls[1], "ln_modulate": ms_cls[2], "gemv_embed": ms_cls[3], "cfg_sampler": ms_cls[4]},
         "step_utilisation": {"F_step_algorithmic": BS * f_step_algorithmic(), "F_step_executed": fx["total"],
