@@ -99,7 +99,7 @@ template <int POLY>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_ns, int stale_max) {
+                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_cycles, int flags) {
     extern __shared__ uint8_t ta_smem_raw[];
     // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
     // access to generic LD/ST instead of LDS/STS)
@@ -257,6 +257,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         const uint32_t pS = smem_u32(smem) + TA_OFF_P + X * TA_P_BYTES + r * 128;   // shared-window address of this row of P
         const int sw = r & 7;
         float m_ref = 0.f;
+        const bool stale_max = (flags & 1) != 0;
         // De-phase the two softmax warpgroups: they share the four MUFU units, so running their exponential phases in
         // lockstep halves each one's rate while the XU idles during their (also simultaneous) load / max / sync phases.
         for (int j = 0; j < nkt; ++j) {
@@ -265,7 +266,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             mbar_wait(&s_full[X], j & 1);
             tc_fence_after();
             if (r == 0) TA_DBG(X, 2);
-            if (X == 1 && j == 0) __nanosleep(stagger_ns);   // small de-phasing of the two warpgroups (measured +1 %)
+            if (X == 1 && j == 0 && stagger_cycles != 0) {
+                // De-phase the two softmax warpgroups once, by a fixed number of cycles.  Warp q of each warpgroup sits on
+                // sub-partition q and the two share its MUFU unit (16 ex2/clk/SM in all; tools/ubench/softmax_loop.cu: 1376 cycles
+                // per 128-exponential row pass for one warp alone, 2436 for two together).  In lockstep both exponentiate at half
+                // rate and then both leave the unit idle through their load / wait phases; half a period apart the phases
+                // interleave: 68 -> 62 us at 1400-1800 cycles, nothing at 1000 or 2200.  A per-tile hand-off (smem counter or
+                // mbarrier between the warpgroups) kept the phase exactly but cost more than the drift it removed (74 us).
+                const long long t_end = clock64() + stagger_cycles;
+                while (clock64() < t_end) {}
+            }
             uint32_t sv[128];
             tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
             tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
@@ -472,7 +482,7 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 64, &mKa)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 16, &mKb)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(vT, static_cast<long long>(B) * H * TA_DHP, NkPad, NkPad, TA_DHP, 64, &mV)) != TPX_OK) return rc;
-    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 4;   // every poly-th exponential on the FMA pipe (0, 3 or 4)
+    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 0;   // every poly-th exponential on the FMA pipe (0, 3 or 4)
     auto kern = poly == 0 ? attention_tc_kernel<0> : (poly == 3 ? attention_tc_kernel<3> : attention_tc_kernel<4>);
     static bool attr_set = false;
     if (!attr_set) {
@@ -482,11 +492,11 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
-    static const unsigned stagger = getenv("TPX_ATT_STAGGER_NS") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER_NS"))) : 800u;
+    static const unsigned stagger = getenv("TPX_ATT_STAGGER") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER"))) : 1600u;   // cycles: initial offset of warpgroup B, about half a key-tile period
     static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
     TPX_CUDA(launch_pdl(kern, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
-                        stale_max));
+                        stale_max ? 1 : 0));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }

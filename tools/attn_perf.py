@@ -1,5 +1,5 @@
 """Device-time the tcgen05 attention kernel on the two DiT shapes (self: 2x16x2048x2048, cross: 1x16x2048x1370, Dh 72).
-Kernel switches are environment variables read once by the library (TPX_ATT_STALE_MAX, TPX_ATT_STAGGER_NS), so run one
+Kernel switches are environment variables read once by the library (TPX_ATT_STALE_MAX, TPX_ATT_STAGGER), so run one
 process per setting."""
 import os
 import sys
@@ -32,4 +32,4 @@ for (B, H, Nq, Nk, Dh, DhP) in [(2, 16, 2048, 2048, 72, 80), (1, 16, 2048, 1370,
     torch.cuda.synchronize()
     us = a.elapsed_time(b) / 50 * 1e3
     res.append(f"Nk={Nk}: {us:6.1f} us {4.0 * B * H * Nq * Nk * Dh / us / 1e6:6.1f} TF/s")
-print(f"stale_max={os.environ.get('TPX_ATT_STALE_MAX', '1')} stagger={os.environ.get('TPX_ATT_STAGGER_NS', '800')}  " + "   ".join(res), flush=True)
+print(f"poly={os.environ.get('TPX_ATT_POLY', '0')} stale_max={os.environ.get('TPX_ATT_STALE_MAX', '1')} stagger={os.environ.get('TPX_ATT_STAGGER', '1600')}  " + "   ".join(res), flush=True)
