@@ -482,12 +482,11 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 64, &mKa)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 16, &mKb)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(vT, static_cast<long long>(B) * H * TA_DHP, NkPad, NkPad, TA_DHP, 64, &mV)) != TPX_OK) return rc;
-    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 0;   // every poly-th exponential on the FMA pipe (0, 3 or 4)
-    auto kern = poly == 0 ? attention_tc_kernel<0> : (poly == 3 ? attention_tc_kernel<3> : attention_tc_kernel<4>);
+    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 0;   // 4: every 4th exponential as a cubic on the FMA pipe — faster in isolation (ubench), slower in the kernel; off
+    auto kern = poly == 0 ? attention_tc_kernel<0> : attention_tc_kernel<4>;
     static bool attr_set = false;
     if (!attr_set) {
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-        TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
     }
