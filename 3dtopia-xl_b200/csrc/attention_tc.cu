@@ -270,9 +270,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 // De-phase the two softmax warpgroups once, by a fixed number of cycles.  Warp q of each warpgroup sits on
                 // sub-partition q and the two share its MUFU unit (16 ex2/clk/SM in all; tools/ubench/softmax_loop.cu: 1376 cycles
                 // per 128-exponential row pass for one warp alone, 2436 for two together).  In lockstep both exponentiate at half
-                // rate and then both leave the unit idle through their load / wait phases; half a period apart the phases
-                // interleave: 68 -> 62 us at 1400-1800 cycles, nothing at 1000 or 2200.  A per-tile hand-off (smem counter or
-                // mbarrier between the warpgroups) kept the phase exactly but cost more than the drift it removed (74 us).
+                // rate and then both leave the unit idle through their load / wait phases; half a tile period apart the phases
+                // interleave and the unit is nearly saturated (2 x 1400 of a ~3000-cycle period): 68 -> 62 us.  The window is
+                // narrow (1400-1800 cycles; nothing at 1000 or 2200) and has to be re-measured when this kernel changes
+                // (tools/attn_perf.py).  Locking the phase on every tile — smem counter, one-way or two-way mbarrier ping-pong,
+                // or starting B when A's first tile is done — cost more than the drift it removes (72-79 us).
                 const long long t_end = clock64() + stagger_cycles;
                 while (clock64() < t_end) {}
             }
@@ -491,7 +493,7 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
-    static const unsigned stagger = getenv("TPX_ATT_STAGGER") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER"))) : 1600u;   // cycles: initial offset of warpgroup B, about half a key-tile period
+    static const unsigned stagger = getenv("TPX_ATT_STAGGER") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER"))) : 1600u;   // cycles; see the de-phasing note in the kernel
     static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
     TPX_CUDA(launch_pdl(kern, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
