@@ -30,7 +30,7 @@ struct tpx_dit {
     // conditioning store
     __half *ck = nullptr, *cv = nullptr, *y16 = nullptr;
     int cond_n = 0, cond_M = 0, cond_MP = 0;
-    bool tc_attn = false;                 // tcgen05 attention (64 < Dh <= 80, N % 8 == 0); V kept transposed
+    bool tc_attn = false;                 // tcgen05 attention (Dh == 72, N % 8 == 0); V kept transposed
 };
 
 static size_t al8(size_t n) { return (n + 7) & ~static_cast<size_t>(7); }
@@ -249,6 +249,7 @@ int tpx_dit_create(const tpx_dit_config* c, tpx_dit** out) {
     TPX_CHECK(c->condition_channels % 8 == 0 && c->mlp_hidden % 8 == 0 && c->out_channels % 8 == 0, TPX_ERR_SHAPE,
               "dit_create: condition/mlp/out channels must be multiples of 8 (%d/%d/%d)", c->condition_channels, c->mlp_hidden, c->out_channels);
     TPX_CHECK(c->depth > 0 && c->seq_length > 0 && c->in_channels > 0, TPX_ERR_SHAPE, "dit_create: non-positive size");
+    TPX_CHECK(c->in_channels % 4 == 0, TPX_ERR_SHAPE, "dit_create: in_channels %d must be a multiple of 4", c->in_channels);
     int rc = tpx_device_check();
     if (rc != TPX_OK) return rc;
     tpx_dit* h = new tpx_dit();
@@ -256,7 +257,7 @@ int tpx_dit_create(const tpx_dit_config* c, tpx_dit** out) {
     h->D = c->hidden_size; h->L = c->depth; h->H = c->num_heads; h->Dm = c->mlp_hidden; h->Dh = Dh;
     h->DhP = Dh <= 16 ? 16 : (Dh <= 32 ? 32 : (Dh <= 64 ? 64 : (Dh <= 80 ? 80 : 128)));
     h->Ltot = h->L * 9 * h->D + 2 * h->D;
-    h->tc_attn = (h->DhP == 80 && h->Dh > 64 && h->N % 8 == 0);
+    h->tc_attn = (h->Dh == 72 && h->N % 8 == 0);   // the tcgen05 kernel keeps the row sums in padding row 72 of the 80-wide tiles
     carve_store(h, nullptr);
     cudaError_t e = cudaMalloc(&h->store, h->store_halves * 2);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(parameter store)"); }

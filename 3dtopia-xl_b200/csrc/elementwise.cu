@@ -229,26 +229,31 @@ int launch_gemv(int in_mode, int out_mode, const __half* W, const __half* bias, 
 // x_embedder: fp32 Linear Cin -> D outside the autocast region (dit_crossattn.py:191).  out rows may be
 // duplicated into a second batch half (forward_with_cfg feeds cat([x, x])).
 // =====================================================================================================
-constexpr int XE_ROWS = 16;
+constexpr int XE_ROWS = 8;
 __global__ void __launch_bounds__(256) x_embed_kernel(const float* __restrict__ x, const __half* __restrict__ W, const __half* __restrict__ bias,
                                                       int rows, int Cin, int D, float* __restrict__ out, long long dup_offset) {
-    extern __shared__ float s_x[];  // [XE_ROWS][Cin]
+    extern __shared__ float4 s_x4[];  // [XE_ROWS][Cin / 4]
+    float* s_x = reinterpret_cast<float*>(s_x4);
     const int r0 = blockIdx.x * XE_ROWS;
     const int nr = min(XE_ROWS, rows - r0);
-    for (int i = threadIdx.x; i < nr * Cin; i += blockDim.x) s_x[i] = x[static_cast<size_t>(r0) * Cin + i];
+    for (int i = threadIdx.x; i < XE_ROWS * Cin; i += blockDim.x) s_x[i] = i < nr * Cin ? x[static_cast<size_t>(r0) * Cin + i] : 0.f;
     __syncthreads();
+    const int C4 = Cin >> 2;
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         float acc[XE_ROWS];
-        const float bj = __half2float(bias[j]);
 #pragma unroll
         for (int r = 0; r < XE_ROWS; ++r) acc[r] = 0.f;
-        const __half* wr = W + static_cast<size_t>(j) * Cin;
-        for (int k = 0; k < Cin; ++k) {
-            const float w = __half2float(wr[k]);
+        const uint2* wr = reinterpret_cast<const uint2*>(W + static_cast<size_t>(j) * Cin);   // Cin % 4 == 0: 8-byte aligned rows
+        for (int k4 = 0; k4 < C4; ++k4) {
+            const uint2 wp = wr[k4];
+            const float2 wa = __half22float2(*reinterpret_cast<const __half2*>(&wp.x)), wb = __half22float2(*reinterpret_cast<const __half2*>(&wp.y));
 #pragma unroll
-            for (int r = 0; r < XE_ROWS; ++r)
-                if (r < nr) acc[r] = fmaf(s_x[r * Cin + k], w, acc[r]);
+            for (int r = 0; r < XE_ROWS; ++r) {
+                const float4 xv = s_x4[r * C4 + k4];       // same address across the warp: one broadcast wavefront
+                acc[r] = fmaf(xv.w, wb.y, fmaf(xv.z, wb.x, fmaf(xv.y, wa.y, fmaf(xv.x, wa.x, acc[r]))));   // k ascending, as before
+            }
         }
+        const float bj = __half2float(bias[j]);
 #pragma unroll
         for (int r = 0; r < XE_ROWS; ++r)
             if (r < nr) {
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(256) x_embed_kernel(const float* __restrict__ 
 
 int launch_x_embed(const float* x, const __half* W, const __half* bias, int rows, int Cin, int D, float* out, long long dup_offset, cudaStream_t st) {
     if (rows <= 0) return TPX_OK;
+    TPX_CHECK(Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0, TPX_ERR_SHAPE, "x_embed: in_channels %d must be a multiple of 4", Cin);
     ProfScope prof(PROF_GEMV, st);
     x_embed_kernel<<<(rows + XE_ROWS - 1) / XE_ROWS, 256, XE_ROWS * Cin * sizeof(float), st>>>(x, W, bias, rows, Cin, D, out, dup_offset);
     TPX_LAUNCH_CHECK();

@@ -144,7 +144,8 @@ int tpx_ln_modulate(float* x, int rows, int D, float eps, const void* shift_f16,
                     int mod_batches, void* out_f16, const void* pre_gate_f16, const void* pre_const_f16, int pre_row0, void* stream);
 /* memory_efficient_attention contract (attention.py:54,109): q [B,H,Nq,DhP], k/v [B,H,Nk,DhP] -> out [B,Nq,H*Dh] */
 int tpx_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Nq, int Nk, int Dh, int DhP, float scale, void* stream);
-/* Same contract on the tcgen05 path (64 < Dh <= 80): q,k [B,H,N,80]; vT = V transposed [B,H,80,NkPad], NkPad % 8 == 0. */
+/* Same contract on the tcgen05 path (Dh == 72, the released model's head size): q,k [B,H,N,80]; vT = V transposed
+ * [B,H,80,NkPad], NkPad % 8 == 0, padding rows/columns finite (row 72 is replaced on chip by ones to produce the row sums). */
 int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale, void* stream);
 /* Same launch with a timeline probe: block 0 writes (tag, clock64) pairs of its MMA thread and of one softmax thread per
  * query tile into timeline_dev (3 x 1024 int64, zero-initialised by the caller).  Tuning aid. */
