@@ -382,10 +382,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--samples-per-gpu", type=int, default=1, help="B per GPU (config #5 uses 4); the headline config is 1")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to fd 1 when
+    # NCCL_DEBUG=VERSION is set on the box), so fd 1 is pointed at stderr for the whole run and the result line goes to the
+    # saved descriptor.
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_fd, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
