@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Time the PrimSDF point query at the reference's mesh-extraction size: 256^3 grid points against 2048 primitives
 (inference.py:108-116 walks them in 8192-point chunks through a dense weight matrix).  Prints ms and points/s; also times
-the oracle's dense torch formulation on the GPU for a 64-chunk sample as the stock-code comparison."""
+a dense [points x prims] torch formulation of the same query on the GPU for a 64-chunk sample as the stock-code comparison
+(restated here; tools do not use oracle/)."""
 import os
 import sys
 import time
@@ -9,8 +10,21 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle  # noqa: E402  (comparison leg only)
 import tpxl_b200  # noqa: E402
+
+
+def dense_query(x, srt, feat, S=8, C=6):
+    """Covered points only (the bulk of the cost): dense weight matrix, gather of the covering (point, prim) pairs, grid_sample."""
+    import torch.nn.functional as F
+    local = (x[:, None, :] - srt[None, :, 1:4]) / srt[None, :, 0:1]
+    w = F.relu(1 - local.abs().amax(-1))
+    w = w / (w.sum(-1, keepdim=True) + 1e-6)
+    ib, ip = torch.where(w > 0)
+    samp = F.grid_sample(feat[ip].reshape(-1, C, S, S, S), local[ib, ip].reshape(-1, 1, 1, 1, 3), mode="bilinear", padding_mode="zeros",
+                         align_corners=True).reshape(-1, C)
+    out = torch.zeros(x.shape[0], C, device=x.device)
+    out.index_add_(0, ib, samp * w[ib, ip][:, None])
+    return out
 
 
 def main():
@@ -42,11 +56,11 @@ def main():
     # stock formulation (dense weight matrix per 8192-point chunk) on the same GPU, 64 chunks
     srt_d, feat_d = m.srt_param.data, m.feat_param.data
     chunks = pts[: 64 * 8192].split(8192)
-    oracle.primsdf.query(chunks[0], srt_d, feat_d)
+    dense_query(chunks[0], srt_d, feat_d)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for c in chunks:
-        oracle.primsdf.query(c, srt_d, feat_d)
+        dense_query(c, srt_d, feat_d)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) * 1e3
     print(f"dense torch formulation on GPU: {dt / 64:.3f} ms per 8192-point chunk -> {dt / 64 * pts.shape[0] / 8192:.0f} ms for the grid")
