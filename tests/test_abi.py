@@ -139,3 +139,18 @@ def test_install_aliases_reference_module_paths():
     assert importlib.import_module("models.vae3d_dib").VAE is tpxl_b200.VAE
     from models.diffusion import create_diffusion
     assert create_diffusion is tpxl_b200.create_diffusion
+
+
+def test_product_and_tools_do_not_use_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__ (build + smoke) and bench.py's CPU legs may touch it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("3dtopia-xl_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+                    if re.search(r"^\s*(import|from)\s+oracle\b", src, re.M) or "oracle/" in src and f.endswith((".cu", ".cuh", ".h")):
+                        offenders.append(os.path.join(sub, f))
+    assert not offenders, offenders
