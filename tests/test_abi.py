@@ -139,6 +139,26 @@ def test_install_aliases_reference_module_paths():
     assert importlib.import_module("models.vae3d_dib").VAE is tpxl_b200.VAE
     from models.diffusion import create_diffusion
     assert create_diffusion is tpxl_b200.create_diffusion
+    assert importlib.import_module("models.primsdf").PrimSDF is tpxl_b200.PrimSDF
+
+
+def test_primsdf_host_contract():
+    """models/primsdf.py:19-50: constructor kwargs of configs/inference_dit.yml:22-30, the two parameters and their slices,
+    load_state_dict / .data reassignment as inference.py:90-103,369 uses them; no CPU compute path."""
+    m = tpxl_b200.PrimSDF(num_prims=32, dim_feat=6, prim_shape=8, init_scale=0.05, sdf2alpha_var=0.005, auto_scale_init=True, init_sampling="uniform")
+    assert list(m.state_dict().keys()) == ["srt_param", "feat_param"]
+    assert tuple(m.srt_param.shape) == (32, 4) and tuple(m.feat_param.shape) == (32, 6 * 512)
+    m.load_state_dict({"srt_param": torch.rand(32, 4), "feat_param": torch.randn(32, 3072)})
+    assert m.feat_geo.shape == (32, 512) and m.feat_tex.shape == (32, 1536) and m.feat_mat.shape == (32, 1024)
+    assert torch.equal(m.pos, m.srt_param[:, 1:4]) and torch.equal(m.scale, m.srt_param[:, 0:1])
+    m.srt_param.data = m.srt_param.data[:7]              # the reference filters primitives in place
+    m.feat_param.data = m.feat_param.data[:7]
+    assert m.srt_param.shape[0] == 7
+    np.testing.assert_allclose(m.sdf2alpha(torch.tensor([0.0, 0.005])).numpy(), [1.0, np.exp(-1.0)], rtol=1e-6)
+    with pytest.raises(tpxl_b200._lib.TpxError):
+        m.eval()(torch.zeros(5, 3))
+    with pytest.raises(ValueError):
+        m(torch.zeros(5, 2))
 
 
 def test_product_and_tools_do_not_use_the_oracle():
