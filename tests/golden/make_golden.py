@@ -78,6 +78,9 @@ def main():
                           num_heads=4, attn_proj_bias=True, cond_drop_prob=0.1, gradient_checkpointing=False), 24, 101),
         ("dit_cfg1", dict(seq_length=256, in_channels=68, condition_channels=768, hidden_size=384, depth=4,
                           num_heads=16, attn_proj_bias=True, cond_drop_prob=0.1, gradient_checkpointing=False), 1370, 102),
+        # the shipped width (D=1152, 16 heads x 72, N=2048, M=1370) with ONE block: pins the 1/72 logits scale, the 9-way
+        # modulation split and the head layout at the real sizes
+        ("dit_full1", dict(synth.FULL_DIT, depth=1), 1370, 104),
     ):
         sd = synth.synth_state_dict(synth.dit_shapes(**cfg), seed)
         model = DiT(**cfg).eval()
@@ -92,6 +95,8 @@ def main():
         for h in hooks:
             h.remove()
         cfg_out = model.forward_with_cfg(x, t, y, cfg_scale=6.0)
+        if tag == "dit_full1":        # keep the fixture small: every 8th token of forward, the full CFG output in fp16-exact halves
+            fwd = fwd[:, ::8]
         np.savez_compressed(os.path.join(OUT, tag + ".npz"), cfg=json.dumps(cfg), M=M, seed=seed, t=t.numpy(),
                             forward=fwd.numpy(), forward_with_cfg=cfg_out.numpy(),
                             blocks=np.stack([b.numpy() for b in blocks]) if tag == "dit_tiny" else np.zeros(0),

@@ -38,3 +38,36 @@ def test_attention_tcgen05_peaky_logits(B, H, Nq, Nk, growth):
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out.float(), ref) < 2e-3
     assert (out.float() - ref).abs().max() < 2e-2
+
+
+def test_full_width_block_against_reference_fixture(golden_dir):
+    """One block at the shipped width against the reference's own fp32 output (tests/golden/dit_full1.npz)."""
+    import json
+    import os
+
+    import numpy as np
+
+    import oracle
+    import tpxl_b200
+    from tpxl_b200 import synth
+    g = np.load(os.path.join(golden_dir, "dit_full1.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    x, y = synth.synth_inputs(1, cfg["seq_length"], cfg["in_channels"], int(g["M"]), cfg["condition_channels"], int(g["seed"]) + 1000)
+    t = torch.from_numpy(g["t"])
+    kw = {k: v for k, v in cfg.items() if k != "gradient_checkpointing"}
+    m = tpxl_b200.DiT(**kw)
+    m.load_state_dict(sd)
+    m = m.to("cuda:0").eval()
+    with torch.no_grad():
+        out = m.forward(x.cuda(), t.cuda(), y.cuda(), torch.float16, True)
+        out_cfg = m.forward_with_cfg(x.cuda(), t.cuda(), y.cuda(), cfg_scale=6.0, precision_dtype=torch.float16, enable_amp=True)
+        sdd = {k: v.cuda() for k, v in sd.items()}
+        o16_cfg = oracle.dit.forward_with_cfg(sdd, x.cuda(), t.cuda(), y.cuda(), 6.0, cfg["num_heads"], "fp16")
+    ref, ref_cfg = torch.from_numpy(g["forward"]).cuda(), torch.from_numpy(g["forward_with_cfg"]).cuda()
+    r = dict(ours_vs_ref32=rel_l2(out.float()[:, ::8], ref), cfg_ours_vs_ref32=rel_l2(out_cfg.float(), ref_cfg),
+             cfg_oracle16_vs_ref32=rel_l2(o16_cfg, ref_cfg), cfg_ours_vs_oracle16=rel_l2(out_cfg.float(), o16_cfg))
+    print(r)
+    assert r["ours_vs_ref32"] < 1e-2 and r["cfg_ours_vs_ref32"] < 1e-2
+    assert r["cfg_ours_vs_oracle16"] < 3e-3
+    assert r["cfg_ours_vs_ref32"] < 2.5 * r["cfg_oracle16_vs_ref32"] + 1e-4

@@ -166,3 +166,19 @@ def test_primsdf_query_matches_reference(golden_dir):
     # training mode leaves uncovered points at zero (primsdf.py:82)
     tr = oracle.primsdf.query(x, srt, feat, inference=False)
     assert float(tr["sdf"][~torch.from_numpy(fx["covered"])].abs().max()) == 0.0
+
+
+def test_dit_full_width_block_matches_reference(golden_dir):
+    """The shipped width (D 1152, 16 heads x 72, 2048 tokens, 1370 context tokens) with one block, against the reference's own
+    output: the logits scale q.k/72, the 9-way modulation split and the head layout at the real sizes."""
+    g = _load(golden_dir, "dit_full1.npz")
+    cfg = json.loads(str(g["cfg"]))
+    assert cfg["hidden_size"] == 1152 and cfg["num_heads"] == 16 and cfg["seq_length"] == 2048 and cfg["depth"] == 1
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), int(g["seed"]))
+    x, y = synth.synth_inputs(1, cfg["seq_length"], cfg["in_channels"], int(g["M"]), cfg["condition_channels"], int(g["seed"]) + 1000)
+    t = torch.from_numpy(g["t"])
+    with torch.no_grad():
+        out = oracle.dit.forward(sd, x, t, y, cfg["num_heads"], "fp32")
+        assert _rel(out[:, ::8], g["forward"]) < 2e-5            # the fixture keeps every 8th token
+        cfg_out = oracle.dit.forward_with_cfg(sd, x, t, y, 6.0, cfg["num_heads"], "fp32")
+        assert _rel(cfg_out, g["forward_with_cfg"]) < 2e-5
