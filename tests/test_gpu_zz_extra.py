@@ -1,5 +1,6 @@
-"""GPU: the rarely-taken paths of the tcgen05 attention kernel (lazy rescale of O in TMEM, redo of a tile against a new row
-maximum, row sums across rescales).  Kept in its own module, collected after the others."""
+"""GPU: tests added after the last GPU session of round 1 (so not yet run on hardware) — the rarely-taken paths of the tcgen05
+attention kernel (lazy rescale of O in TMEM, redo of a tile against a new row maximum, row sums across rescales) and one block
+at the shipped width against the reference fixture.  Kept in their own module, collected after the validated ones."""
 import pytest
 import torch
 
