@@ -49,26 +49,19 @@ class PrimSDF(nn.Module):
     def sdf2alpha(self, sdf):
         return torch.exp(-(sdf / self.sdf2alpha_var) ** 2)
 
-    @property
-    def pos(self):
-        return self.srt_param[:, 1:4]
 
-    @property
-    def scale(self):
-        return self.srt_param[:, 0:1]
+def _column_view(param: str, lo, hi):
+    """Read-only views of the two parameters under the reference's attribute names (models/primsdf.py:111-137).  ``lo`` / ``hi``
+    are column bounds, or names of the per-instance ``*_start_index`` / ``*_end_index`` attributes."""
+    def get(self):
+        a = getattr(self, lo) if isinstance(lo, str) else lo
+        b = getattr(self, hi) if isinstance(hi, str) else hi
+        return getattr(self, param)[:, a:b]
+    return property(get)
 
-    @property
-    def feat(self):
-        return self.feat_param
 
-    @property
-    def feat_geo(self):
-        return self.feat_param[:, self.geo_start_index:self.geo_end_index]
-
-    @property
-    def feat_tex(self):
-        return self.feat_param[:, self.tex_start_index:self.tex_end_index]
-
-    @property
-    def feat_mat(self):
-        return self.feat_param[:, self.mat_start_index:self.mat_end_index]
+for _name, _param, _lo, _hi in (("pos", "srt_param", 1, 4), ("scale", "srt_param", 0, 1), ("feat", "feat_param", 0, None),
+                                ("feat_geo", "feat_param", "geo_start_index", "geo_end_index"),
+                                ("feat_tex", "feat_param", "tex_start_index", "tex_end_index"),
+                                ("feat_mat", "feat_param", "mat_start_index", "mat_end_index")):
+    setattr(PrimSDF, _name, _column_view(_param, _lo, _hi))
