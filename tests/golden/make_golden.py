@@ -133,6 +133,16 @@ def main():
     traj = [o for o in d10.p_sample_loop_progressive(tiny_model.forward_with_cfg, x.shape, x, clip_denoised=False,
                                                      model_kwargs=kw, progress=False, device="cpu")]
     fx["ddpm10_samples"] = np.stack([o["sample"].numpy() for o in traj])
+    # respacing strings through the reference's own space_timesteps (respace.py:12-62), incl. the cases it rejects
+    from models.diffusion.respace import space_timesteps
+    cases = {}
+    for spec in ("ddim10", "ddim20", "ddim40", "ddim125", "ddim500", "ddim1000", "ddim600", "ddim999", "1", "7", "250", "1000", "10,10,5", "1,1,1,1",
+                 "3,0,7", "400,300,200", "2000", "334,334,334"):
+        try:
+            cases[spec] = sorted(int(v) for v in space_timesteps(1000, spec))
+        except ValueError:
+            cases[spec] = "ValueError"
+    fx["space_cases"] = json.dumps(cases)
     np.savez_compressed(os.path.join(OUT, "sampler.npz"), **fx)
     print("sampler", fx["map_ddim25"][:4], fx["ddim25_samples"].shape)
 

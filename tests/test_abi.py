@@ -174,3 +174,17 @@ def test_product_and_tools_do_not_use_the_oracle():
                     if re.search(r"^\s*(import|from)\s+oracle\b", src, re.M) or "oracle/" in src and f.endswith((".cu", ".cuh", ".h")):
                         offenders.append(os.path.join(sub, f))
     assert not offenders, offenders
+
+
+def test_respacing_strings_match_reference(golden_dir):
+    """respace.py:12-62 through the reference itself: 'ddimK' strides, section counts, and the specs it rejects."""
+    fx = np.load(os.path.join(golden_dir, "sampler.npz"))
+    cases = json.loads(str(fx["space_cases"]))
+    from tpxl_b200.diffusion import space_timesteps
+    assert len(cases) >= 18
+    for spec, want in cases.items():
+        if want == "ValueError":
+            with pytest.raises(ValueError):
+                space_timesteps(1000, spec)
+        else:
+            assert sorted(space_timesteps(1000, spec)) == want, spec

@@ -182,3 +182,14 @@ def test_dit_full_width_block_matches_reference(golden_dir):
         assert _rel(out[:, ::8], g["forward"]) < 2e-5            # the fixture keeps every 8th token
         cfg_out = oracle.dit.forward_with_cfg(sd, x, t, y, 6.0, cfg["num_heads"], "fp32")
         assert _rel(cfg_out, g["forward_with_cfg"]) < 2e-5
+
+
+def test_oracle_respacing_matches_reference(golden_dir):
+    fx = _load(golden_dir, "sampler.npz")
+    cases = json.loads(str(fx["space_cases"]))
+    for spec, want in cases.items():
+        if want == "ValueError":
+            with pytest.raises(ValueError):
+                oracle.diffusion.kept_timesteps(1000, spec)
+        else:
+            assert sorted(oracle.diffusion.kept_timesteps(1000, spec)) == want, spec
