@@ -133,6 +133,9 @@ def main():
     traj = [o for o in d10.p_sample_loop_progressive(tiny_model.forward_with_cfg, x.shape, x, clip_denoised=False,
                                                      model_kwargs=kw, progress=False, device="cpu")]
     fx["ddpm10_samples"] = np.stack([o["sample"].numpy() for o in traj])
+    dl = create_diffusion(timestep_respacing="ddim50", noise_schedule="linear", diffusion_steps=1000, parameterization="v")
+    fx["acp_linear_ddim50"] = dl.alphas_cumprod
+    fx["map_linear_ddim50"] = np.array(dl.timestep_map)
     # respacing strings through the reference's own space_timesteps (respace.py:12-62), incl. the cases it rejects
     from models.diffusion.respace import space_timesteps
     cases = {}

@@ -79,6 +79,9 @@ def test_schedule_matches_reference_fixture(golden_dir):
     d25 = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
     for nm in ("posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "sqrt_recipm1_alphas_cumprod"):
         np.testing.assert_allclose(getattr(d25, nm), g[nm + "_ddim25"], rtol=1e-12)
+    dl = tpxl_b200.create_diffusion("ddim50", noise_schedule="linear", diffusion_steps=1000, parameterization="v")
+    assert np.array_equal(np.array(dl.timestep_map), g["map_linear_ddim50"])
+    np.testing.assert_allclose(dl.alphas_cumprod, g["acp_linear_ddim50"], rtol=1e-12)
     with pytest.raises(NotImplementedError):
         tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="eps")
     with pytest.raises(NotImplementedError):

@@ -79,6 +79,9 @@ def test_schedule_tables_and_timestep_maps(golden_dir):
         np.testing.assert_allclose(s.alphas_cumprod, g[f"acp_ddim{k}"], rtol=1e-13, atol=0)
     full = oracle.diffusion.Schedule("")
     np.testing.assert_allclose(full.alphas_cumprod, g["acp_full"], rtol=1e-13)
+    lin = oracle.diffusion.Schedule("ddim50", noise_schedule="linear")
+    assert lin.timestep_map == list(g["map_linear_ddim50"])
+    np.testing.assert_allclose(lin.alphas_cumprod, g["acp_linear_ddim50"], rtol=1e-12)
     np.testing.assert_allclose(full.betas, g["betas_full"], rtol=1e-12)
     assert np.array_equal(np.array(oracle.diffusion.Schedule("10").timestep_map), g["map_sec10"])
     s = oracle.diffusion.Schedule("ddim25")
