@@ -36,3 +36,19 @@ def test_product_arm_has_no_cpu_path():
     p = _run("--steps", "1", "--warmup", "0", "--no-cpu", "--no-vae", timeout=300)
     assert p.returncode != 0
     assert p.stdout.strip() == ""
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: rank 0 alone measures and prints; the other rank exits 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
