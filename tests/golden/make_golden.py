@@ -187,6 +187,35 @@ def main():
                         sdf=preds["sdf"].numpy(), tex=preds["tex"].numpy(), mat=preds["mat"].numpy())
     print("primsdf", int(covered.sum()), "of", len(pts), "points covered")
 
+    # ---- DINOv2 ViT-B/14-reg encoder: the reference wrapper, random weights instead of the hub download --------
+    sys.path.insert(0, ROOT)
+    import oracle                                                            # noqa: E402  (weight synthesis shared with the tests)
+    from models.conditioner.image_dinov2 import Dinov2Wrapper               # noqa: E402
+    import models.conditioner.dinov2.hub.backbones as bb                     # noqa: E402
+    Dinov2Wrapper._build_dinov2 = staticmethod(lambda model_name, modulation_dim=None, pretrained=True:
+                                               getattr(bb, model_name)(modulation_dim=modulation_dim, pretrained=False))
+    enc = Dinov2Wrapper("dinov2_vitb14_reg", freeze=True).eval()
+    sd = oracle.dinov2.synth_weights(105)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}, "DINOv2 key/shape contract drifted"
+    assert list(enc.state_dict().keys()) == list(sd.keys())
+    enc.load_state_dict(sd, strict=True)
+    rs = np.random.RandomState(1105)
+    # a smooth synthetic picture + noise, 0..255, the 518 x 518 the pipeline feeds (configs/inference_dit.yml:18-19)
+    yy, xx = np.meshgrid(np.linspace(0, 1, 518), np.linspace(0, 1, 518), indexing="ij")
+    img = np.stack([127 + 100 * np.sin(6 * xx + 2 * yy), 127 + 100 * np.cos(5 * yy), 255 * xx * yy], -1) + 12 * rs.standard_normal((518, 518, 3))
+    img = np.clip(img, 0, 255).astype(np.float32)[None]
+    blocks = []
+    hooks = [b.register_forward_hook(lambda m_, i_, o_: blocks.append(o_.clone())) for b in enc.model.blocks]
+    out = enc(torch.from_numpy(img))
+    for h in hooks:
+        h.remove()
+    small = np.clip(img[:, ::2, ::2][:, :224, :224], 0, 255)                # a 224 x 224 picture: exercises Resize(518, bicubic)
+    out_small = enc(torch.from_numpy(np.ascontiguousarray(small)))
+    np.savez_compressed(os.path.join(OUT, "dinov2.npz"), seed=105, img_seed=1105, out=out.numpy()[:, ::6], out_small=out_small.numpy()[:, ::24],
+                        block_stats=np.array([[float(b.double().mean()), float(b.double().abs().mean()), float(b.double().std())] for b in blocks]),
+                        block0_slice=blocks[0][0, :8, :16].numpy(), block11_slice=blocks[11][0, 5:13, :16].numpy())
+    print("dinov2", tuple(out.shape), float(out.abs().mean()), float(out_small.abs().mean()))
+
 
 if __name__ == "__main__":
     main()

@@ -196,3 +196,24 @@ def test_oracle_respacing_matches_reference(golden_dir):
                 oracle.diffusion.kept_timesteps(1000, spec)
         else:
             assert sorted(oracle.diffusion.kept_timesteps(1000, spec)) == want, spec
+
+
+def test_dinov2_encoder_matches_reference(golden_dir):
+    """oracle/dinov2.py against the reference's own Dinov2Wrapper('dinov2_vitb14_reg') (image_dinov2.py:44-61) with synthetic
+    weights: full 518 x 518 input (every 6th output token stored), per-block statistics, and a 224 x 224 input through the
+    bicubic antialiased Resize."""
+    g = _load(golden_dir, "dinov2.npz")
+    sd = oracle.dinov2.synth_weights(int(g["seed"]))
+    rs = np.random.RandomState(int(g["img_seed"]))
+    yy, xx = np.meshgrid(np.linspace(0, 1, 518), np.linspace(0, 1, 518), indexing="ij")
+    img = np.stack([127 + 100 * np.sin(6 * xx + 2 * yy), 127 + 100 * np.cos(5 * yy), 255 * xx * yy], -1) + 12 * rs.standard_normal((518, 518, 3))
+    img = np.clip(img, 0, 255).astype(np.float32)[None]
+    with torch.no_grad():
+        out, blocks = oracle.dinov2.forward(sd, torch.from_numpy(img), return_blocks=True)
+        assert tuple(out.shape) == (1, 1370, 768)
+        assert _rel(out[:, ::6], g["out"]) < 2e-5
+        stats = np.array([[float(b.double().mean()), float(b.double().abs().mean()), float(b.double().std())] for b in blocks])
+        np.testing.assert_allclose(stats, g["block_stats"], rtol=1e-4, atol=1e-6)
+        assert _rel(blocks[0][0, :8, :16], g["block0_slice"]) < 1e-5 and _rel(blocks[11][0, 5:13, :16], g["block11_slice"]) < 2e-5
+        small = np.ascontiguousarray(np.clip(img[:, ::2, ::2][:, :224, :224], 0, 255))
+        assert _rel(oracle.dinov2.forward(sd, torch.from_numpy(small))[:, ::24], g["out_small"]) < 2e-5
