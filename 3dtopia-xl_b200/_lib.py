@@ -63,6 +63,7 @@ SIGNATURES = {
     "tpx_attention_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "tpx_attention_tc_debug": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "tpx_cfg_combine": (_i, [_vp, _i64, _f, _vp, _vp]),
+    "tpx_gelu_erf": (_i, [_vp, _i64, _vp]),
     "tpx_primsdf_query": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "tpx_groupnorm_silu": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "tpx_conv3d_k3": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),

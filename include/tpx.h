@@ -171,6 +171,10 @@ int tpx_conv3d_k3(const void* x_f16, const void* W_f16, const void* bias_f16, co
 int tpx_primsdf_query(const float* x_dev, const float* srt_dev, const float* feat_dev, int64_t n, int K, int S, int dim_feat, int inference,
                       float* out_dev, void* stream);
 
+/* nn.GELU() (erf form) in place on an fp16 tensor of n elements (n % 8 == 0, 16-B aligned) — the activation of the DINOv2 MLP
+ * (models/conditioner/dinov2/layers/mlp.py:33-39); the rest of that encoder is built from the entry points above. */
+int tpx_gelu_erf(void* x_f16, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,36 @@ def test_full_width_block_against_reference_fixture(golden_dir):
     assert r["ours_vs_ref32"] < 1e-2 and r["cfg_ours_vs_ref32"] < 1e-2
     assert r["cfg_ours_vs_oracle16"] < 3e-3
     assert r["cfg_ours_vs_ref32"] < 4 * r["cfg_oracle16_vs_ref32"] + 5e-4      # no further from fp32 than the fp16 contract itself
+
+
+def test_dinov2_encoder_against_reference_fixture(golden_dir):
+    """The DINOv2 ViT-B/14-reg mirror (built from the DiT kernels + tpx_gelu_erf) against the reference wrapper's fp32 output.
+    Tolerance 5e-3 relative L2: fp16-input GEMMs against an fp32 reference (the CPU emulation of the same contract sits at ~1e-3)."""
+    import importlib
+    import os
+
+    import numpy as np
+
+    import oracle
+    d = importlib.import_module("tpxl_b200.dinov2")
+    g = np.load(os.path.join(golden_dir, "dinov2.npz"))
+    sd = oracle.dinov2.synth_weights(int(g["seed"]))
+    rs = np.random.RandomState(int(g["img_seed"]))
+    yy, xx = np.meshgrid(np.linspace(0, 1, 518), np.linspace(0, 1, 518), indexing="ij")
+    img = np.stack([127 + 100 * np.sin(6 * xx + 2 * yy), 127 + 100 * np.cos(5 * yy), 255 * xx * yy], -1) + 12 * rs.standard_normal((518, 518, 3))
+    img = np.clip(img, 0, 255).astype(np.float32)[None]
+    m = d.Dinov2Wrapper("dinov2_vitb14_reg", freeze=True)
+    m.load_state_dict(sd)
+    m = m.to("cuda:0").eval()
+    with torch.no_grad():
+        out = m(torch.from_numpy(img).cuda())
+        small = np.ascontiguousarray(np.clip(img[:, ::2, ::2][:, :224, :224], 0, 255))
+        out_small = m(torch.from_numpy(small).cuda())
+        two = m(torch.from_numpy(np.concatenate([img, img[:, ::-1].copy()], 0)).cuda())        # batch of 2: per-picture token blocks
+    torch.cuda.synchronize()
+    assert out.shape == (1, 1370, 768) and out.dtype == torch.float32
+    r = dict(full=rel_l2(out[:, ::6], torch.from_numpy(g["out"]).cuda()), small=rel_l2(out_small[:, ::24], torch.from_numpy(g["out_small"]).cuda()),
+             batch=rel_l2(two[0:1], out))
+    print(r)
+    assert r["full"] < 5e-3 and r["small"] < 5e-3
+    assert r["batch"] < 1e-6                                   # the same picture gives the same tokens whatever shares the batch
