@@ -69,6 +69,8 @@ class Dinov2Wrapper(nn.Module):
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         state_dict = {k: v for k, v in state_dict.items() if "mask_token" not in k}      # dropped by the reference too (hub/backbones.py)
+        if state_dict and not any(k.startswith("model.") for k in state_dict):           # a hub checkpoint of the bare ViT (no wrapper prefix)
+            state_dict = {"model." + k: v for k, v in state_dict.items()}
         missing = [k for k in self._shapes if k not in state_dict]
         unexpected = [k for k in state_dict if k not in self._shapes]
         bad = [k for k, shp in self._shapes.items() if k in state_dict and tuple(state_dict[k].shape) != tuple(shp)]

@@ -37,6 +37,9 @@ def test_state_dict_contract_and_errors():
     sd = oracle.dinov2.synth_weights(3)
     sd["model.mask_token"] = torch.zeros(1, 768)                 # present in hub checkpoints, dropped by the reference loader
     m.load_state_dict(sd)
+    bare = {k[len("model."):]: v for k, v in sd.items()}           # dinov2_vitb14_reg4_pretrain.pth has no wrapper prefix
+    m.load_state_dict(bare)
+    assert torch.equal(m.state_dict()["model.norm.weight"], sd["model.norm.weight"])
     with pytest.raises(RuntimeError):
         m.load_state_dict({k: v for k, v in sd.items() if "ls1" not in k})
     with pytest.raises(NotImplementedError):
