@@ -49,6 +49,8 @@ SIGNATURES = {
     "tpx_dit_forward": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "tpx_dit_debug_residual": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tpx_sampler_step": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, C.POINTER(SamplerCoefs), _vp, _vp, _vp]),
+    "tpx_latent_split": (_i, [_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp]),
+    "tpx_primvolume_pack": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp]),
     "tpx_vae_create": (_i, [C.POINTER(VaeConfig), C.POINTER(_vp)]),
     "tpx_vae_destroy": (None, [_vp]),
     "tpx_vae_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),

@@ -27,6 +27,7 @@ struct tpx_dit {
     std::vector<uint8_t> seen;            // per required key
     std::vector<std::string> required;
     bool finalized = false;
+    bool has_null = false;                // null_cond_embedding given (cond_drop_prob > 0 models only; dit_crossattn.py:143-146)
     // conditioning store
     __half *ck = nullptr, *cv = nullptr, *y16 = nullptr;
     int cond_n = 0, cond_M = 0, cond_MP = 0;
@@ -124,7 +125,8 @@ bool find_slot(tpx_dit* h, const std::string& key, Slot* s) {
 
 void build_required(tpx_dit* h) {
     auto& r = h->required;
-    for (const char* k : {"null_cond_embedding", "x_embedder.weight", "x_embedder.bias", "t_embedder.mlp.0.weight", "t_embedder.mlp.0.bias",
+    // null_cond_embedding is optional: the reference only creates it when cond_drop_prob > 0 (dit_crossattn.py:143-146)
+    for (const char* k : {"x_embedder.weight", "x_embedder.bias", "t_embedder.mlp.0.weight", "t_embedder.mlp.0.bias",
                           "t_embedder.mlp.2.weight", "t_embedder.mlp.2.bias", "final_layer.linear.weight", "final_layer.linear.bias",
                           "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias"})
         r.emplace_back(k);
@@ -288,6 +290,7 @@ int tpx_dit_set_weight(tpx_dit* h, const char* ref_key, const void* dev_ptr, int
     if (rc != TPX_OK) return rc;
     for (size_t i = 0; i < h->required.size(); ++i)
         if (h->required[i] == key) h->seen[i] = 1;
+    if (key == "null_cond_embedding") h->has_null = true;
     h->finalized = false;
     return TPX_OK;
 }
@@ -298,7 +301,7 @@ int tpx_dit_finalize(tpx_dit* h, void* stream) {
         TPX_CHECK(h->seen[i], TPX_ERR_STATE, "dit_finalize: missing key '%s' in state_dict", h->required[i].c_str());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // per-block constant of cross-attention against an all-null context: h(Wp . h(Wv . null + bv) + bp)
-    for (int i = 0; i < h->L; ++i) {
+    for (int i = 0; h->has_null && i < h->L; ++i) {
         const DitLayer& l = h->layers[i];
         int rc = launch_gemv(GEMV_IN_F16, GEMV_OUT_F16, l.Wkv + static_cast<size_t>(h->D) * h->Dc, l.bkv + h->D, h->null16, nullptr, 1, h->D, h->Dc,
                              h->tmp_v, nullptr, h->D, st);
@@ -366,6 +369,7 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     TPX_CHECK(h->finalized, TPX_ERR_STATE, "dit_forward: weights not finalized");
     TPX_CHECK(B >= 1 && B <= 8, TPX_ERR_SHAPE, "dit_forward: batch %d must be in [1,8]", B);
     TPX_CHECK(use_cfg >= 0 && use_cfg <= 2, TPX_ERR_ARG, "dit_forward: use_cfg %d", use_cfg);
+    TPX_CHECK(use_cfg == 0 || h->has_null, TPX_ERR_STATE, "dit_forward: classifier-free guidance needs null_cond_embedding (model built with cond_drop_prob = 0)");
     const int S = use_cfg ? 2 * B : B;       // sequences in the batch
     const int Sc = use_cfg == 1 ? B : S;     // leading sequences with real cross-attention
     TPX_CHECK(h->ck != nullptr && h->cond_n == Sc, TPX_ERR_STATE, "dit_forward: conditioning holds %d sequences, this call needs %d (call set_cond)",
@@ -483,6 +487,19 @@ int tpx_sampler_step(int ddim, const float* x, const void* mo, int mo_dtype, con
     static_assert(sizeof(SamplerCoefs) == sizeof(tpx_sampler_coefs), "coef struct mirror");
     memcpy(&c, k, sizeof(c));
     return launch_sampler_step(ddim, x, mo, mo_dtype == TPX_DTYPE_F16, noise, n, C, c, x_prev, x0, static_cast<cudaStream_t>(stream));
+}
+
+int tpx_latent_split(const float* sample, const float* mean, const float* stdv, float inv_nf, int64_t T, int C, float* srt, float* z, void* stream) {
+    TPX_CHECK(sample != nullptr && srt != nullptr && z != nullptr, TPX_ERR_ARG, "latent_split: null argument");
+    TPX_CHECK((mean == nullptr) == (stdv == nullptr), TPX_ERR_ARG, "latent_split: latent_mean and latent_std go together");
+    TPX_CHECK(T >= 0 && C > 4, TPX_ERR_SHAPE, "latent_split: need more than 4 channels (got %d)", C);
+    return launch_latent_split(sample, mean, stdv, inv_nf, T, C, srt, z, static_cast<cudaStream_t>(stream));
+}
+
+int tpx_primvolume_pack(const float* srt, const void* decoded, int decoded_dtype, int64_t T, int F, int vox, int srt_fix, float* out, void* stream) {
+    TPX_CHECK(srt != nullptr && decoded != nullptr && out != nullptr, TPX_ERR_ARG, "primvolume_pack: null argument");
+    TPX_CHECK(decoded_dtype == TPX_DTYPE_F32 || decoded_dtype == TPX_DTYPE_F16, TPX_ERR_ARG, "primvolume_pack: dtype %d", decoded_dtype);
+    return launch_primvolume_pack(srt, decoded, decoded_dtype == TPX_DTYPE_F16, T, F, vox, srt_fix, out, static_cast<cudaStream_t>(stream));
 }
 
 int tpx_linear(const void* A, int lda, const void* W, const void* bias, void* out, int ldo, int M, int N, int K, int act, float post_scale, int tile_n,

@@ -414,4 +414,81 @@ int launch_fill_rows_half(const __half* vec, __half* dst, long long rows, int K,
     return TPX_OK;
 }
 
+// =====================================================================================================
+// Sample -> decode glue.  Index layout is the contract with PrimSDF / the ray-marcher and is
+// bit-exact; the arithmetic repeats the reference's eager CUDA ops one rounding at a time (a tensor divided by a Python
+// scalar is a multiplication by the fp32 reciprocal on CUDA).
+//   a13  inference.py:328-332, app.py:119-123 : v = x / latent_nf * latent_std + latent_mean ; srt = v[..., 0:4], z = v[..., 4:]
+//        (without per-channel statistics: srt = x[..., 0:4], z = x[..., 4:] / latent_nf ; inference.py:337)
+//   a15  inference.py:343-348, app.py:134-139 : feat[:, 0] /= 5 ; feat[:, 1:] = (feat[:, 1:] + 1) / 2 ; channel-major reshape ;
+//        concat [srt | feat] -> [T, 4 + 6*512]   (without per-channel statistics: srt[..., 0] = srt[..., 0] / 10 + 0.05)
+// =====================================================================================================
+__global__ void latent_split_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv, float inv_nf,
+                                    long long T, int C, float* __restrict__ srt, float* __restrict__ z) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= T * C) return;
+    const long long tok = i / C;
+    const int c = static_cast<int>(i - tok * C);
+    float v = x[i];
+    if (mean != nullptr) v = __fadd_rn(__fmul_rn(__fmul_rn(v, inv_nf), stdv[c]), mean[c]);
+    else if (c >= 4) v = __fmul_rn(v, inv_nf);
+    if (c < 4) srt[tok * 4 + c] = v;
+    else z[tok * (C - 4) + (c - 4)] = v;
+}
+
+int launch_latent_split(const float* x, const float* mean, const float* stdv, float inv_nf, long long T, int C, float* srt, float* z, cudaStream_t st) {
+    const long long n = T * C;
+    if (n <= 0) return TPX_OK;
+    ProfScope prof(PROF_ELEMWISE, st);
+    latent_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, mean, stdv, inv_nf, T, C, srt, z);
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
+template <typename T_IN>
+__global__ void primvolume_pack_kernel(const float* __restrict__ srt, const T_IN* __restrict__ dec, long long T, int F, int vox, int srt_fix,
+                                       float* __restrict__ out) {
+    // one thread per 4 consecutive output floats; rows are 4 + F floats, F % 4 == 0 -> every group is 16-B aligned on both sides
+    const int groups_per_row = 1 + F / 4;
+    const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gi >= T * groups_per_row) return;
+    const long long tok = gi / groups_per_row;
+    const int g = static_cast<int>(gi - tok * groups_per_row);
+    float4 o;
+    if (g == 0) {
+        o = *reinterpret_cast<const float4*>(srt + tok * 4);
+        if (srt_fix) o.x = __fadd_rn(__fmul_rn(o.x, 0.1f), 0.05f);
+    } else {
+        const int f = (g - 1) * 4;              // feature index = channel * vox + voxel (channel-major, inference.py:347)
+        const bool sdf = f < vox;               // channel 0
+        float v[4];
+        if constexpr (sizeof(T_IN) == 4) {
+            const float4 d = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dec) + tok * F + f);
+            v[0] = d.x; v[1] = d.y; v[2] = d.z; v[3] = d.w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = sdf ? __fmul_rn(v[k], 0.2f) : __fmul_rn(__fadd_rn(v[k], 1.0f), 0.5f);
+        } else {
+            const uint2 d = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dec) + tok * F + f);
+            const __half2 a = *reinterpret_cast<const __half2*>(&d.x), b = *reinterpret_cast<const __half2*>(&d.y);
+            v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = sdf ? h2f_round(__fmul_rn(v[k], 0.2f)) : h2f_round(__fmul_rn(h2f_round(__fadd_rn(v[k], 1.0f)), 0.5f));
+        }
+        o = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    *reinterpret_cast<float4*>(out + tok * (4 + F) + g * 4) = o;
+}
+
+int launch_primvolume_pack(const float* srt, const void* dec, int dec_is_half, long long T, int F, int vox, int srt_fix, float* out, cudaStream_t st) {
+    TPX_CHECK(F % 4 == 0 && vox % 4 == 0 && vox <= F, TPX_ERR_SHAPE, "primvolume_pack: feature length %d / voxel count %d must be multiples of 4", F, vox);
+    const long long n = T * (1 + F / 4);
+    if (n <= 0) return TPX_OK;
+    ProfScope prof(PROF_ELEMWISE, st);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (dec_is_half) primvolume_pack_kernel<__half><<<grid, 256, 0, st>>>(srt, static_cast<const __half*>(dec), T, F, vox, srt_fix, out);
+    else primvolume_pack_kernel<float><<<grid, 256, 0, st>>>(srt, static_cast<const float*>(dec), T, F, vox, srt_fix, out);
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
 }  // namespace tpx

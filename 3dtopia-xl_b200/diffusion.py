@@ -134,7 +134,11 @@ class SpacedDiffusion:
         lib = _lib.lib()
         mo = model_out if model_out.dtype in (torch.float16, torch.float32) else model_out.float()
         mo = mo.contiguous()
-        xx = x.contiguous()
+        if x.device.type != "cuda" or mo.device != x.device:
+            raise _lib.TpxError("sampler step: x and the model output must live on the same CUDA device (no CPU path)")
+        xx = x.to(torch.float32).contiguous()       # the kernel reads fp32 (the reference promotes to fp32 through its fp32 coefficient tensors)
+        if noise is not None:
+            noise = noise.to(device=x.device, dtype=torch.float32).contiguous()
         x_prev, x0 = torch.empty_like(xx), torch.empty_like(xx)
         k = self.step_coefs(i, eta, clip_denoised)
         need_noise = (not ddim) or float(k.sigma) != 0.0

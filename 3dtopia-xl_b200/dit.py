@@ -9,7 +9,7 @@ What is different underneath (results stay within the fp16 tolerance of the refe
   * parameters live once, as fp16, in a packed store owned by the C library (the reference keeps fp32
     modules and lets autocast re-cast ~905 M weights every forward);
   * cross-attention K/V of all blocks are computed once per conditioning tensor ``y`` and cached
-    (keyed on the tensor's storage pointer + version counter), not once per step;
+    (the cache holds a strong reference to that tensor and compares identity + version counter), not once per step;
   * under ``forward_with_cfg`` the null-conditioned half of the batch does not run cross-attention at
     all: with an all-equal context the softmax is uniform and the branch equals a per-block constant.
 """
@@ -52,6 +52,7 @@ class DiT(nn.Module):
         self._ws: Dict[int, torch.Tensor] = {}
         self._cond_ws: Optional[torch.Tensor] = None
         self._cond_key = None
+        self._cond_ref: Optional[torch.Tensor] = None   # strong reference to the cached y: its address cannot be recycled while cached
         self.collapse_null_branch = True     # set False to run the null half through real cross-attention (tests)
 
     # ---- parameters: reference key names, values kept as given (CPU or GPU, fp16 or fp32) ----------------
@@ -113,7 +114,7 @@ class DiT(nn.Module):
             _lib.check(lib.tpx_dit_create(C.byref(cfg), C.byref(h)), "tpx_dit_create")
         self._handle, self._handle_device = h, dev
         self._ws.clear()
-        self._cond_ws, self._cond_key = None, None
+        self._cond_ws, self._cond_key, self._cond_ref = None, None, None
         self._ingest()
 
     def _ingest(self):
@@ -134,7 +135,7 @@ class DiT(nn.Module):
                 _lib.check(lib.tpx_dit_set_weight(self._handle, k.encode(), t.data_ptr(), _lib.dtype_tag(t), shape, t.dim(), st), f"set_weight({k})")
             _lib.check(lib.tpx_dit_finalize(self._handle, st), "tpx_dit_finalize")
             torch.cuda.current_stream().synchronize()
-        self._cond_key = None
+        self._cond_key, self._cond_ref = None, None
 
     def _destroy_handle(self):
         if self.__dict__.get("_handle") is not None:
@@ -165,9 +166,13 @@ class DiT(nn.Module):
         return (t.data_ptr() + 255) & ~255
 
     def _set_cond(self, y: torch.Tensor, with_null: bool):
-        """(Re)compute the hoisted cross-attention K/V when the conditioning tensor changed."""
-        key = (y.data_ptr(), y._version, tuple(y.shape), y.dtype, with_null)
-        if key == self._cond_key:
+        """(Re)compute the hoisted cross-attention K/V when the conditioning tensor changed.
+
+        Identity of the cached conditioning = the tensor OBJECT (held alive here, so the caching allocator cannot hand its
+        address to a later request's tensor — app.py:108-131 builds a fresh function-local y per request) + its version
+        counter (in-place edits) + the view geometry (a different slice of the same storage is a different y)."""
+        key = (y.data_ptr(), y._version, tuple(y.shape), tuple(y.stride()), y.dtype, with_null)
+        if self._cond_ref is not None and key == self._cond_key and (y is self._cond_ref or y.untyped_storage().data_ptr() == self._cond_ref.untyped_storage().data_ptr()):
             return
         lib = _lib.lib()
         yy = y.detach().to(self._handle_device, torch.float32).contiguous()
@@ -179,7 +184,7 @@ class DiT(nn.Module):
         if self._cond_ws is None or self._cond_ws.numel() < nbytes + 256:
             self._cond_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._handle_device)
         _lib.check(lib.tpx_dit_set_cond(self._handle, yy.data_ptr(), n_cross, M, self._aligned(self._cond_ws), nbytes, _lib.stream_ptr()), "tpx_dit_set_cond")
-        self._cond_key = key
+        self._cond_key, self._cond_ref = key, y
 
     def _run(self, x, t, y, use_cfg: int, cfg_scale: float, enable_amp: bool):
         self._require_handle()
@@ -187,6 +192,10 @@ class DiT(nn.Module):
             raise ValueError(f"x must be [B,{self.seq_length},{self.in_channels}], got {tuple(x.shape)}")
         if y.dim() != 3 or y.shape[0] != x.shape[0] or y.shape[2] != self.condition_channels:
             raise ValueError(f"y must be [B,M,{self.condition_channels}] with B={x.shape[0]}, got {tuple(y.shape)}")
+        if not 1 <= x.shape[0] <= 8:
+            raise _lib.TpxError(f"batch of {x.shape[0]} samples per forward: the B200 DiT handle runs 1..8 samples (2..16 sequences under CFG) per call; split larger batches")
+        if use_cfg and self.cond_drop_prob <= 0:
+            raise AttributeError("'DiT' object has no attribute 'null_cond_embedding'")   # as the reference would (dit_crossattn.py:208)
         lib = _lib.lib()
         dev = self._handle_device
         with torch.cuda.device(dev):
@@ -206,14 +215,27 @@ class DiT(nn.Module):
         return out if enable_amp else out.float()
 
     def forward(self, x, t, y, precision_dtype=torch.float32, enable_amp=False):
-        """DiT.forward (dit_crossattn.py:184-202).  The kernels always compute in the reference's fp16-autocast
-        contract; with enable_amp=False the result is returned as fp32."""
+        """DiT.forward (dit_crossattn.py:184-202).
+
+        PRECISION: the kernels implement ONE contract, the reference's CUDA autocast(fp16) path (what inference.py / app.py run:
+        ``precision: fp16`` + ``amp``).  ``enable_amp=False`` or ``precision_dtype != float16`` does NOT select an fp32 (or bf16)
+        computation here: the same fp16-contract result is returned, cast to fp32 when amp is off, and a warning says so once."""
+        self._precision_notice(precision_dtype, enable_amp)
         return self._run(x, t, y, 0, 0.0, enable_amp)
 
+    _warned_precision = False
+
+    def _precision_notice(self, precision_dtype, enable_amp):
+        if (not enable_amp or precision_dtype not in (torch.float16, None)) and not DiT._warned_precision:
+            DiT._warned_precision = True
+            import warnings
+            warnings.warn("tpxl_b200.DiT computes in the reference's fp16-autocast contract regardless of precision_dtype/enable_amp "
+                          f"(got precision_dtype={precision_dtype}, enable_amp={enable_amp}); the output is fp16-accurate, returned as "
+                          f"{'fp16' if enable_amp else 'fp32'}", stacklevel=3)
+
     def forward_with_cfg(self, x, t, y, cfg_scale=0.0, precision_dtype=torch.float32, enable_amp=False):
-        """DiT.forward_with_cfg (dit_crossattn.py:204-213)."""
-        if self.cond_drop_prob <= 0:
-            raise AttributeError("'DiT' object has no attribute 'null_cond_embedding'")   # as the reference would
+        """DiT.forward_with_cfg (dit_crossattn.py:204-213).  Precision: see forward()."""
+        self._precision_notice(precision_dtype, enable_amp)
         return self._run(x, t, y, 1 if self.collapse_null_branch else 2, cfg_scale, enable_amp)
 
     def debug_residual(self, n_seq: int) -> torch.Tensor:

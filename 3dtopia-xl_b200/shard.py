@@ -71,3 +71,25 @@ def run_sharded(num_samples: int, per_sample: Callable[[int, torch.Tensor], torc
         probe = per_sample(0, noise[0:1].to(device) if device is not None else noise[0:1])
         local = probe[:0]
     return gather_to_rank0(local, num_samples, group)
+
+
+def run_sharded_batched(num_samples: int, per_batch: Callable[[List[int], torch.Tensor], torch.Tensor], batch: int = 1,
+                        noise: Optional[torch.Tensor] = None, seed: int = 42, num_prims: int = 2048, channels: int = 68, group=None) -> Optional[torch.Tensor]:
+    """Like run_sharded, with the samples a rank owns grouped `batch` at a time into one call
+    `per_batch(indices, x_T[len(indices), P, C]) -> tensor[len(indices), ...]` (config #5: 4 samples per GPU share one forward,
+    8 sequences under CFG).  The sample -> rank assignment and the noise stream are those of run_sharded, so the result for sample s
+    does not depend on `batch` or on the number of ranks beyond the kernels' batch-invariance (tests/test_gpu_dit.py)."""
+    if batch < 1:
+        raise ValueError("batch must be >= 1")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if noise is None:
+        noise = draw_noise(num_samples, num_prims, channels, seed)
+    mine = assigned(num_samples, world, rank)
+    outs = [per_batch(mine[i:i + batch], noise[mine[i:i + batch]]) for i in range(0, len(mine), batch)]
+    if outs:
+        local = torch.cat(outs, 0)
+    else:                                   # more ranks than samples: this rank still joins the gather with an empty block
+        probe = per_batch([0], noise[0:1])
+        local = probe[:0]
+    return gather_to_rank0(local, num_samples, group)

@@ -103,6 +103,21 @@ int tpx_sampler_step(int ddim, const float* x_dev, const void* model_out_dev, in
                      const tpx_sampler_coefs* k, float* x_prev_dev, float* pred_x0_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Sample -> decode glue — inference.py:328-332,343-348 ; app.py:119-123,134-139
+ * ---------------------------------------------------------------------------------------------------------- */
+/* a13: sample device fp32 [T, C] (T = batch * num_prims, C = 68).  With per-channel statistics (mean/std device fp32 [C]):
+ * v = sample * inv_nf * std + mean, one rounding per op as the reference's eager CUDA ops (x / python_float = x * fp32(1/nf));
+ * without (mean == std == NULL): srt = sample[:, 0:4], z = sample[:, 4:] * inv_nf (inference.py:337).
+ * Outputs: srt device fp32 [T, 4] = (scale, xyz), z device fp32 [T, C-4] = the [T,1,4,4,4] latents VAE.decode takes. */
+int tpx_latent_split(const float* sample_dev, const float* mean_dev, const float* std_dev, float inv_nf, int64_t T, int C, float* srt_dev,
+                     float* z_dev, void* stream);
+/* a15: decoded device [T, F] (F = 6 * vox, NCDHW per primitive = channel-major; dtype fp32 or fp16) -> out device fp32 [T, 4 + F] =
+ * [srt | sdf/5 | (rgb+1)/2 | (mat+1)/2], the PrimSDF / ray-marcher layout (models/primsdf.py:28-33).  srt_fix != 0 applies
+ * srt[:, 0] = srt[:, 0] / 10 + 0.05 (checkpoints without per-channel statistics, inference.py:343-344). */
+int tpx_primvolume_pack(const float* srt_dev, const void* decoded_dev, int decoded_dtype, int64_t T, int F, int vox, int srt_fix, float* out_dev,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * VAE decoder — models/vae3d_dib.py:391-440 (class VAE), :330-387 (Decoder)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct tpx_vae tpx_vae;

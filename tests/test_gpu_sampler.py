@@ -70,6 +70,60 @@ def test_conditioning_cache_tracks_tensor_identity_and_version():
     assert torch.equal(e, f)
 
 
+def test_conditioning_cache_survives_address_reuse_between_requests():
+    """app.py:108-131: every request builds a fresh function-local y against a module-level model.  After request 1's y is
+    freed the caching allocator hands the SAME address to request 2's y (same shape, version 0) — the hoisted K/V must still be
+    recomputed.  The cache holds a strong reference to the tensor it was computed from, so the address cannot be recycled."""
+    sd, m, x, _ = _setup(57)
+    t = torch.tensor([480, 480], device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(58)
+    with torch.no_grad():
+        y1 = torch.randn(2, 77, 768, generator=g, device=DEV)
+        vals2 = torch.randn(2, 77, 768, generator=g, device=DEV).cpu()
+        m.forward_with_cfg(x, t, y1, cfg_scale=3.0, enable_amp=True)
+        p1 = y1.data_ptr()
+        del y1                                             # request 1 returns: its y dies
+        y2 = torch.empty(2, 77, 768, device=DEV)           # request 2: the allocator would reuse the freed block if nothing held it
+        y2.copy_(vals2)
+        reused = y2.data_ptr() == p1
+        got = m.forward_with_cfg(x, t, y2, cfg_scale=3.0, enable_amp=True).clone()
+        fresh = tpxl_b200.DiT(**CFG)
+        fresh.load_state_dict(sd)
+        fresh = fresh.to(DEV).eval()
+        want = fresh.forward_with_cfg(x, t, y2, cfg_scale=3.0, enable_amp=True)
+    print("address reused by the allocator:", reused)
+    assert not reused                                      # the cached tensor is held alive, so its block was not handed out again
+    assert torch.equal(got, want)
+    # and the situation the bug needs — same address, same shape, version 0, different values — as a direct check
+    with torch.no_grad():
+        m._cond_ref = None                                 # drop the strong reference (what round 1 effectively did) ...
+        y3 = torch.empty(2, 77, 768, device=DEV)
+        y3.copy_(vals2 * 0.5)
+        got3 = m.forward_with_cfg(x, t, y3, cfg_scale=3.0, enable_amp=True)     # ... a cache without a live reference never hits
+        want3 = fresh.forward_with_cfg(x, t, y3, cfg_scale=3.0, enable_amp=True)
+    assert torch.equal(got3, want3)
+
+
+def test_model_without_null_embedding_runs_plain_forward():
+    """cond_drop_prob = 0 (the constructor default, as in the reference): no null_cond_embedding exists; forward() works,
+    forward_with_cfg raises like the reference's attribute lookup would (dit_crossattn.py:208)."""
+    import oracle
+    cfg = dict(CFG, cond_drop_prob=0.0)
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), 59)
+    assert "null_cond_embedding" not in sd
+    m = tpxl_b200.DiT(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x, y = synth.synth_inputs(1, cfg["seq_length"], cfg["in_channels"], 77, cfg["condition_channels"], 60)
+    t = torch.tensor([200], device=DEV)
+    with torch.no_grad():
+        out = m.forward(x.to(DEV), t, y.to(DEV), torch.float16, True)
+        ref = oracle.dit.forward({k: v.to(DEV) for k, v in sd.items()}, x.to(DEV), t, y.to(DEV), cfg["num_heads"], "fp16")
+    assert rel_l2(out.float(), ref) < 3e-3
+    with pytest.raises(AttributeError):
+        m.forward_with_cfg(x.to(DEV), t, y.to(DEV), cfg_scale=2.0, enable_amp=True)
+
+
 def test_full_size_ddim_properties():
     """Shipped size, full depth: determinism, finite outputs, and sample-index independence (one sample alone ==
     the same sample inside a batch of two) — the property the one-sample-per-GPU sharding rests on."""

@@ -72,10 +72,14 @@ def test_decode_full_batch_properties():
         full = vae.decode(z)
         again = vae.decode(z)
         part = vae.decode(z[1000:1007].contiguous())
-        ref = oracle.vae.decode({k: v.to(DEV) for k, v in sd.items()}, z[1000:1007], "fp32")
+        sub = z[3::8].contiguous()                          # 256 primitives strided over the whole batch, against the oracle
+        ref = oracle.vae.decode({k: v.to(DEV) for k, v in sd.items()}, sub, "fp32")
     assert torch.isfinite(full).all() and torch.equal(full, again)
     assert torch.equal(part, full[1000:1007])
-    assert rel_l2(part, ref) < 1e-2
+    got = full[3::8]
+    per_prim = (got - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1).clamp_min(1e-20)
+    print("256 strided primitives vs oracle fp32: rel-L2", rel_l2(got, ref), "worst primitive", float(per_prim.max()))
+    assert rel_l2(got, ref) < 1e-2 and float(per_prim.max()) < 3e-2
 
 
 def test_error_paths():

