@@ -42,6 +42,7 @@ SIGNATURES = {
     "tpx_dit_create": (_i, [C.POINTER(DitConfig), C.POINTER(_vp)]),
     "tpx_dit_destroy": (None, [_vp]),
     "tpx_dit_set_weight": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64), _i, _vp]),
+    "tpx_dit_get_weight": (_i, [_vp, C.c_char_p, _vp, _i, _vp]),
     "tpx_dit_finalize": (_i, [_vp, _vp]),
     "tpx_dit_cond_bytes": (_sz, [_vp, _i, _i]),
     "tpx_dit_workspace_bytes": (_sz, [_vp, _i]),

@@ -295,6 +295,13 @@ int tpx_dit_set_weight(tpx_dit* h, const char* ref_key, const void* dev_ptr, int
     return TPX_OK;
 }
 
+int tpx_dit_get_weight(tpx_dit* h, const char* ref_key, void* dst_dev, int dtype, void* stream) {
+    TPX_CHECK(h != nullptr && ref_key != nullptr && dst_dev != nullptr, TPX_ERR_ARG, "dit_get_weight: null argument");
+    Slot s;
+    if (!find_slot(h, std::string(ref_key), &s)) { set_error("dit_get_weight: unexpected key '%s'", ref_key); return TPX_ERR_KEY; }
+    return launch_from_half(s.ptr, dst_dev, dtype, s.d1 == 0 ? s.d0 : s.d0 * s.d1, static_cast<cudaStream_t>(stream));
+}
+
 int tpx_dit_finalize(tpx_dit* h, void* stream) {
     TPX_CHECK(h != nullptr, TPX_ERR_ARG, "dit_finalize: null handle");
     for (size_t i = 0; i < h->required.size(); ++i)

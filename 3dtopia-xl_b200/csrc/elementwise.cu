@@ -401,6 +401,27 @@ int launch_to_half(const void* src, int src_dtype, __half* dst, long long n, cud
     return TPX_OK;
 }
 
+// packed fp16 slot -> fp32 / fp16 tensor (state_dict() export of a handle whose host copy was released)
+template <typename T>
+__global__ void from_half_kernel(const __half* __restrict__ src, T* __restrict__ dst, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = static_cast<T>(__half2float(src[i]));
+}
+template <>
+__global__ void from_half_kernel<__half>(const __half* __restrict__ src, __half* __restrict__ dst, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+int launch_from_half(const __half* src, void* dst, int dst_dtype, long long n, cudaStream_t st) {
+    if (n <= 0) return TPX_OK;
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (dst_dtype == TPX_DTYPE_F32) from_half_kernel<float><<<grid, 256, 0, st>>>(src, static_cast<float*>(dst), n);
+    else if (dst_dtype == TPX_DTYPE_F16) from_half_kernel<__half><<<grid, 256, 0, st>>>(src, static_cast<__half*>(dst), n);
+    else { set_error("from_half: unsupported destination dtype %d", dst_dtype); return TPX_ERR_ARG; }
+    TPX_LAUNCH_CHECK();
+    return TPX_OK;
+}
+
 // rows of `src` [rows, K] broadcast of one vector: dst[r,:] = h(vec)  (null-conditioning context rows)
 __global__ void fill_rows_half_kernel(const __half* __restrict__ vec, __half* __restrict__ dst, long long rows, int K) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

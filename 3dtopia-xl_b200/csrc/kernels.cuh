@@ -28,6 +28,7 @@ int launch_cfg_combine(const __half* both, long long n_half, float s, __half* ou
 int launch_sampler_step(int ddim, const float* x, const void* mo, int mo_is_half, const float* noise, long long n, int C, const SamplerCoefs& k,
                         float* x_prev, float* x0_out, cudaStream_t st);
 int launch_to_half(const void* src, int src_dtype, __half* dst, long long n, cudaStream_t st);
+int launch_from_half(const __half* src, void* dst, int dst_dtype, long long n, cudaStream_t st);
 int launch_latent_split(const float* x, const float* mean, const float* stdv, float inv_nf, long long T, int C, float* srt, float* z, cudaStream_t st);
 int launch_primvolume_pack(const float* srt, const void* dec, int dec_is_half, long long T, int F, int vox, int srt_fix, float* out, cudaStream_t st);
 int launch_fill_rows_half(const __half* vec, __half* dst, long long rows, int K, cudaStream_t st);

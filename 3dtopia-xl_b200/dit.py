@@ -52,6 +52,7 @@ class DiT(nn.Module):
         self._ws: Dict[int, torch.Tensor] = {}
         self._cond_ws: Optional[torch.Tensor] = None
         self._cond_key = None
+        self._resident_only = False                     # True once the host copy was released (release_state_dict / load_checkpoint)
         self._cond_ref: Optional[torch.Tensor] = None   # strong reference to the cached y: its address cannot be recycled while cached
         self.collapse_null_branch = True     # set False to run the null half through real cross-attention (tests)
 
@@ -73,9 +74,46 @@ class DiT(nn.Module):
         return sd
 
     def state_dict(self, *args, **kwargs):
+        if self._sd is None and self._handle is not None and self._resident_only:
+            return self._export_all()              # host copy released: read the packed fp16 store back (reference key names / shapes)
         if self._sd is None:
             self._sd = self._default_init()
         return OrderedDict(self._sd)
+
+    # ---- checkpoint ingestion without a retained copy (inference.py:257-265) ------------------------
+    def _export(self, key: str, dtype=torch.float16) -> torch.Tensor:
+        t = torch.empty(self._shapes[key], dtype=dtype, device=self._handle_device)
+        with torch.cuda.device(self._handle_device):
+            _lib.check(_lib.lib().tpx_dit_get_weight(self._handle, key.encode(), t.data_ptr(), _lib.dtype_tag(t), _lib.stream_ptr()), f"get_weight({key})")
+        return t
+
+    def _export_all(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((k, self._export(k)) for k in self._shapes)
+
+    def _param(self, key: str) -> torch.Tensor:
+        return self._sd[key] if self._sd is not None else self._export(key, torch.float32)
+
+    def release_state_dict(self) -> None:
+        """Drop the host mirror's references to the checkpoint tensors.  The packed fp16 store in the C library (1.8 GB for the shipped
+        model) is then the only copy; ``state_dict()`` and ``.to(other_gpu)`` read it back through ``tpx_dit_get_weight``."""
+        self._require_handle()
+        self._sd, self._resident_only = None, True
+
+    def load_checkpoint(self, path: str, key: Optional[str] = "ema", retain: bool = False):
+        """``model.load_state_dict(torch.load(path, map_location='cpu')['ema'])`` (inference.py:260-262) without materialising the
+        checkpoint twice: the file is memory-mapped, every tensor goes host -> device -> packed fp16 slot one at a time (fp16
+        checkpoints such as model_sview_dit_fp16.pt are copied, never widened to fp32 modules), and with ``retain=False`` nothing but
+        the packed store is kept.  The model must already be on its GPU (``.to('cuda')``)."""
+        self._require_handle()
+        try:
+            ck = torch.load(path, map_location="cpu", mmap=True, weights_only=True)
+        except (RuntimeError, ValueError, TypeError):      # legacy (non-zipfile) serialisation cannot be memory-mapped
+            ck = torch.load(path, map_location="cpu", weights_only=True)
+        sd = ck[key] if key is not None else ck
+        out = self.load_state_dict(sd)                     # validates keys / shapes, ingests tensor by tensor
+        if not retain:
+            self.release_state_dict()
+        return out
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         missing = [k for k in self._shapes if k not in state_dict]
@@ -88,11 +126,11 @@ class DiT(nn.Module):
             errs.append(f"Missing key(s): {missing[:5]}{'...' if len(missing) > 5 else ''}; unexpected key(s): {unexpected[:5]}")
         if errs:
             raise RuntimeError("Error(s) in loading state_dict for DiT:\n\t" + "\n\t".join(errs))
-        base = self._sd if self._sd is not None else (self._default_init() if missing else OrderedDict())
+        base = self._sd if self._sd is not None else ((self._export_all() if self._resident_only and self._handle is not None else self._default_init()) if missing else OrderedDict())
         sd = OrderedDict()
         for k in self._shapes:
             sd[k] = state_dict[k].detach() if k in state_dict else base[k]
-        self._sd = sd
+        self._sd, self._resident_only = sd, False
         if self._handle is not None:
             self._ingest()
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
@@ -106,6 +144,9 @@ class DiT(nn.Module):
 
     def _create_handle(self, dev: torch.device):
         lib = _lib.lib()
+        if self._sd is None and self._resident_only and self._handle is not None:
+            self._sd = self._export_all()          # moving a released model to another GPU: carry the packed values over
+            torch.cuda.synchronize(self._handle_device)
         self._destroy_handle()
         cfg = _lib.DitConfig(self.seq_length, self.in_channels, self.out_channels, self.condition_channels, self.hidden_size, self.depth,
                              self.num_heads, self.mlp_hidden)
@@ -122,6 +163,7 @@ class DiT(nn.Module):
         if self._sd is None:
             self._sd = self._default_init()
         dev = self._handle_device
+        released = self._resident_only
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
             keep = []
@@ -136,6 +178,8 @@ class DiT(nn.Module):
             _lib.check(lib.tpx_dit_finalize(self._handle, st), "tpx_dit_finalize")
             torch.cuda.current_stream().synchronize()
         self._cond_key, self._cond_ref = None, None
+        if released:                               # re-ingested after a device move of a released model: release again
+            self._sd = None
 
     def _destroy_handle(self):
         if self.__dict__.get("_handle") is not None:
@@ -177,7 +221,7 @@ class DiT(nn.Module):
         lib = _lib.lib()
         yy = y.detach().to(self._handle_device, torch.float32).contiguous()
         if with_null:
-            null = self._sd["null_cond_embedding"].to(self._handle_device, torch.float32)
+            null = self._param("null_cond_embedding").to(self._handle_device, torch.float32)
             yy = torch.cat([yy, null.expand_as(yy)], dim=0).contiguous()
         n_cross, M = yy.shape[0], yy.shape[1]
         nbytes = lib.tpx_dit_cond_bytes(self._handle, n_cross, M)

@@ -61,6 +61,16 @@ class VAE(nn.Module):
             self._ingest()
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
+    def load_checkpoint(self, path: str, key: Optional[str] = "model_state_dict"):
+        """``vae.load_state_dict(torch.load(path, map_location='cpu')['model_state_dict'])`` (inference.py:257-258) from a memory-mapped
+        file: only decoder.* / post_quant_conv.* tensors are read and uploaded (the encoder half of the checkpoint is never touched)."""
+        try:
+            ck = torch.load(path, map_location="cpu", mmap=True, weights_only=True)
+        except (RuntimeError, ValueError, TypeError):
+            ck = torch.load(path, map_location="cpu", weights_only=True)
+        sd = ck[key] if key is not None else ck
+        return self.load_state_dict(OrderedDict((k, v) for k, v in sd.items() if not k.startswith(("encoder.", "quant_conv."))))
+
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         dev = self._anchor.device

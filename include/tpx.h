@@ -63,6 +63,10 @@ void tpx_dit_destroy(tpx_dit* h);
  * ("blocks.3.crossattn.to_q.weight", "final_layer.linear.bias", "null_cond_embedding", ...).  `dev_ptr` is a
  * contiguous device tensor of dtype TPX_DTYPE_*; shape is checked against the module tree.  Unknown key -> TPX_ERR_KEY. */
 int tpx_dit_set_weight(tpx_dit* h, const char* ref_key, const void* dev_ptr, int dtype, const int64_t* shape, int ndim, void* stream);
+/* Read a parameter back from the packed store (fp16 values, written as `dtype`) into dst_dev (same element count as the key's
+ * reference shape).  Lets the host mirror drop its copy of the checkpoint after ingestion and still answer
+ * state_dict() / move between devices. */
+int tpx_dit_get_weight(tpx_dit* h, const char* ref_key, void* dst_dev, int dtype, void* stream);
 /* Call once after the last set_weight: checks every required key arrived, derives the per-block constant of the
  * all-null cross-attention (proj(to_v(null_cond_embedding))). */
 int tpx_dit_finalize(tpx_dit* h, void* stream);

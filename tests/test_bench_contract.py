@@ -24,7 +24,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["unit"] == "steps/s" and d["vs_baseline"] is None and "workload" in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json"))
+    assert cb["kind"] == ("reference" if staged else "port") and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
+    assert d["extrapolated"] is False and d["same_config"] is True and d["measured_blocks"] == 28      # whole 28-block steps, not a depth sample
     assert abs(d["value"] * d["ms_per_step"] - 1000.0) < 1e-6 * 1000.0        # steps/s and ms/step describe the same run
 
 

@@ -143,3 +143,38 @@ def test_full_model_full_size_against_oracle_and_batch_of_four():
     assert r["ours_vs_o16"] < 5e-3                      # 28 blocks deep, CFG 6: fp16 noise of both sides, amplified
     assert r["ours_vs_o32"] < 2.5 * r["o16_vs_o32"] + 1e-4
     assert r["batch_vs_single"] < 1e-3
+
+
+def test_checkpoint_ingestion_from_file_without_retained_copy(tmp_path):
+    """an fp16 checkpoint file ({'ema': state_dict}, like model_sview_dit_fp16.pt) goes file -> packed device store with
+    no retained copy; the result equals the load_state_dict path, and state_dict() still answers (read back from the device)."""
+    cfg = dict(seq_length=128, in_channels=68, condition_channels=768, hidden_size=384, depth=2, num_heads=16, attn_proj_bias=True, cond_drop_prob=0.1)
+    sd = synth.synth_state_dict(synth.dit_shapes(**cfg), 47)
+    path = os.path.join(tmp_path, "dit_fp16.pt")
+    torch.save({"ema": {k: v.half() for k, v in sd.items()}, "step": 1}, path)
+    a = _model(cfg, sd)
+    b = tpxl_b200.DiT(**cfg).to(DEV).eval()
+    b.load_checkpoint(path)
+    assert b._sd is None                                            # nothing but the packed store is kept
+    x, y = synth.synth_inputs(1, 128, 68, 77, 768, 48)
+    t = torch.tensor([480], device=DEV)
+    with torch.no_grad():
+        oa = a.forward_with_cfg(x.to(DEV), t, y.to(DEV), cfg_scale=6.0, enable_amp=True)
+        ob = b.forward_with_cfg(x.to(DEV), t, y.to(DEV), cfg_scale=6.0, enable_amp=True)
+    assert torch.equal(oa, ob)
+    back = b.state_dict()
+    assert list(back) == list(sd) and all(torch.equal(back[k].cpu(), sd[k].half()) for k in sd)
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("x_embedder.bias")
+        b.load_state_dict(bad)
+    v = tpxl_b200.VAE(**synth.FULL_VAE).to(DEV)
+    vsd = synth.synth_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 49)
+    vpath = os.path.join(tmp_path, "vae_fp16.pt")
+    torch.save({"model_state_dict": dict({k: w.half() for k, w in vsd.items()}, **{"encoder.conv_in.weight": torch.zeros(4, 4)})}, vpath)
+    v.load_checkpoint(vpath)
+    w = tpxl_b200.VAE(**synth.FULL_VAE)
+    w.load_state_dict(vsd)
+    w = w.to(DEV)
+    z = torch.randn(3, 1, 4, 4, 4, device=DEV)
+    assert torch.equal(v.decode(z), w.decode(z))
