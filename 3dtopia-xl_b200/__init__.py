@@ -9,7 +9,7 @@ import types
 
 from . import synth  # noqa: F401
 from . import _lib  # noqa: F401
-from . import diffusion, dinov2, dit, pipeline, primsdf, vae  # noqa: F401
+from . import diffusion, dinov2, dit, pipeline, primsdf, shard, vae  # noqa: F401
 from .diffusion import SpacedDiffusion, create_diffusion  # noqa: F401
 from .dit import DiT  # noqa: F401
 from .pipeline import LatentCodec, PrimXPipeline  # noqa: F401
