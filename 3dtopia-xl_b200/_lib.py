@@ -65,6 +65,7 @@ SIGNATURES = {
     "tpx_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "tpx_attention_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "tpx_attention_tc_debug": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "tpx_debug_gemm_timeline": (_i, [_vp]),
     "tpx_cfg_combine": (_i, [_vp, _i64, _f, _vp, _vp]),
     "tpx_gelu_erf": (_i, [_vp, _i64, _vp]),
     "tpx_primsdf_query": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),

@@ -576,6 +576,11 @@ int tpx_attention_tc_debug(const void* q, const void* k, const void* vT, void* o
                                Nq, Nk, NkPad, Dh, scale, static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(timeline_dev));
 }
 
+int tpx_debug_gemm_timeline(int64_t* timeline_dev) {
+    tpx::set_gemm_timeline(reinterpret_cast<long long*>(timeline_dev));
+    return TPX_OK;
+}
+
 int tpx_cfg_combine(const void* both, int64_t n_half, float s, void* out, void* stream) {
     TPX_CHECK(both != nullptr && out != nullptr, TPX_ERR_ARG, "cfg_combine: null argument");
     return launch_cfg_combine(static_cast<const __half*>(both), n_half, s, static_cast<__half*>(out), static_cast<cudaStream_t>(stream));

@@ -70,6 +70,10 @@ int prof_end(float* ms_by_class, long long* n_by_class) {
     return TPX_OK;
 }
 
+// timeline probe target of the next GEMM launches (tools/gemm_timeline.py); nullptr = off
+static long long* g_gemm_dbg = nullptr;
+void set_gemm_timeline(long long* dev_buf) { g_gemm_dbg = dev_buf; }
+
 int gemm_num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -220,6 +224,7 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     a.M = p.M;
     a.N = p.N;
     a.num_kb = (p.K + bk - 1) / bk;
+    a.dbg = g_gemm_dbg;
     a.conv_S = p.conv_S;
     a.chunks_per_tap = p.a_mode == AMODE_CONV3 ? p.conv_C / bk : 1;
     CUtensorMap ta, tb;

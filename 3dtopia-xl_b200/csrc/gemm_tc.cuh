@@ -45,6 +45,7 @@ struct GemmArgs {
     float alpha;
     float* out32;
     int n_valid, S3;
+    long long* dbg;   // timeline probe (tpx_debug_gemm_timeline): 16 int64 per CTA, nullptr in the product path
 };
 
 template <int BN, int BK>
@@ -290,8 +291,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    long long* const dbg = g.dbg != nullptr ? g.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long t_entry = dbg != nullptr ? clock64() : 0;
     pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
     pdl_wait();                // ... and ours ends here: the operands written by the previous kernel are now visible
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[0] = clock64(); dbg[11] = static_cast<long long>(gt); dbg[13] = t_entry;
+    }
 
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + 127) / 128;
@@ -302,10 +310,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // warp-converged producer: every lane follows the ring, one elected lane arms the barrier and issues the TMA
         int stage = 0;
         uint32_t phase = 0;
+        long long w_empty = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             for (int kb = 0; kb < num_kb; ++kb) {
+                const long long tw = dbg != nullptr ? clock64() : 0;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (dbg != nullptr) w_empty += clock64() - tw;
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -326,6 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (dbg != nullptr && lane == 0) { dbg[5] = w_empty; dbg[6] = clock64(); }
     } else if (warp == 1) {
         // The whole warp runs this loop with warp-uniform control flow and one elected lane issues: descriptors and
         // the TMEM address then live in uniform registers, which keeps the tcgen05.mma issue rate high.
@@ -336,12 +348,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long w_full = 0, w_tempty = 0, t_first = 0;
+        int ntile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            long long tw = dbg != nullptr ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            if (dbg != nullptr) w_tempty += clock64() - tw;
             tc_fence_after();
             const uint32_t tmem_d = tmem_u + acc * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
+                tw = dbg != nullptr ? clock64() : 0;
                 mbar_wait(&full_bar[stage], phase);
+                if (dbg != nullptr) { const long long tn = clock64(); w_full += tn - tw; if (ntile == 0 && kb == 0) t_first = tn; }
                 tc_fence_after();
                 const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
                 const uint64_t adesc = umma_desc_kmajor<Cfg::SW>(a_addr);
@@ -357,13 +375,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ++ntile;
         }
+        if (dbg != nullptr && lane == 0) { dbg[1] = t_first; dbg[2] = clock64(); dbg[3] = w_full; dbg[4] = w_tempty; dbg[10] = ntile; }
     } else if (warp >= 4) {
         const int quad = warp & 3;
         const int et = threadIdx.x - 128;
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool gate_in_smem = (EPI == EPI_GATED) && (g.rows_per_batch % 128 == 0);
+        long long w_tfull = 0, t_proc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             const int n0 = n_blk * BN;
@@ -393,7 +414,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 hc.n = row - hc.b * g.Nseq;
                 head_row_off = (static_cast<size_t>(hc.b) * g.H * g.Nseq + hc.n) * g.DhP;
             }
+            const long long tw = dbg != nullptr ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
+            const long long tp = dbg != nullptr ? clock64() : 0;
+            w_tfull += tp - tw;
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
             constexpr int CH = BN >= 32 ? 32 : 16;
@@ -407,11 +431,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
+            if (dbg != nullptr) t_proc += clock64() - tp;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (dbg != nullptr && et == 0) { dbg[7] = w_tfull; dbg[8] = t_proc; dbg[9] = clock64(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[12] = static_cast<long long>(gt); dbg[14] = clock64(); dbg[15] = smid;
+    }
     if (warp == 2) {
         __syncwarp();
         tc_fence_after();

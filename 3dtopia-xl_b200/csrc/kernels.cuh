@@ -43,6 +43,8 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
 // gemm_tc.cu : cached 2-D TMA descriptor over a row-major fp16 matrix (swizzle = box_cols * 2 bytes: 128/64/32)
 int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out);
 
+void set_gemm_timeline(long long* dev_buf);
+
 // vae_kernels.cu
 int launch_vae_conv_in(const void* z, int z_dtype, const __half* w_pq, const __half* b_pq, const __half* W, const __half* bias, int P, int C,
                        __half* out, cudaStream_t st);

@@ -170,6 +170,10 @@ int tpx_attention_tc(const void* q, const void* k, const void* vT, void* out, in
  * query tile into timeline_dev (3 x 1024 int64, zero-initialised by the caller).  Tuning aid. */
 int tpx_attention_tc_debug(const void* q, const void* k, const void* vT, void* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
                             int64_t* timeline_dev, void* stream);
+/* Timeline probe of the tcgen05 GEMM (tuning aid, tools/gemm_timeline.py): while timeline_dev is non-null every later GEMM
+ * launch makes CTA b write 16 int64 at timeline_dev[16 b ..]: clock64 stamps of its producer / MMA / epilogue roles and the
+ * cycles each spent waiting on its mbarriers.  NULL switches it off (the default). */
+int tpx_debug_gemm_timeline(int64_t* timeline_dev);
 /* out = h(uncond + h(s * h(cond - uncond)))  over [cond; uncond] halves of n_half elements (dit_crossattn.py:210-213) */
 int tpx_cfg_combine(const void* both_f16, int64_t n_half, float s, void* out_f16, void* stream);
 /* GroupNorm(groups, eps, affine) [+ SiLU] on a channels-last fp16 volume [P, S3, C]  (vae3d_dib.py:109,112,131-139) */
