@@ -403,6 +403,9 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         ++op_index;                                                                                               \
     } while (0)
 
+    // The head-split GEMM epilogues write only the Dh real columns of each 80-wide head row (24-column bulk stores); the padding
+    // columns / rows of q, k, v(T) must be zero, so the three buffers (contiguous in the workspace) are cleared once per forward.
+    TPX_CUDA(cudaMemsetAsync(w.q, 0, reinterpret_cast<uint8_t*>(w.ao) - reinterpret_cast<uint8_t*>(w.q), st));
     // timestep embedding (fp32) -> silu -> fp16, then every adaLN modulation of the network in one GEMV pass
     TPX_RC(launch_gemv(GEMV_IN_TIMESTEP, GEMV_OUT_F32_SILU, h->Wt0, h->bt0, nullptr, reinterpret_cast<const long long*>(t), B, D, 256, w.th1, nullptr, D, st));
     TPX_RC(launch_gemv(GEMV_IN_F32, GEMV_OUT_F32_AND_SILU16, h->Wt2, h->bt2, w.th1, nullptr, B, D, D, w.temb, w.ts16, D, st));
@@ -420,8 +423,8 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         {
             GemmArgs a{};
             a.bias = l.bq; a.post_scale = qscale; a.out0 = w.q;
-            a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N;
-            TPX_RC(gemm_linear(w.h16, D, l.Wq, Sc * N, D, D, EPI_HEADS, a, 0, st));
+            a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N; a.heads_tma = 1;
+            TPX_RC(gemm_linear(w.h16, D, l.Wq, Sc * N, D, D, EPI_HEADS, a, D % 144 == 0 && h->Dh % 24 == 0 ? 144 : 0, st));
         }
         if (h->tc_attn) TPX_RC(launch_attention_tc(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_v, w.ao, Sc, h->H, N, M, h->cond_MP, h->Dh, qscale, st));
         else TPX_RC(launch_attention(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_kv, w.ao, Sc, h->H, N, M, h->Dh, h->DhP, qscale, st));
@@ -437,7 +440,7 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         {
             GemmArgs a{};
             a.bias = l.bqkv; a.post_scale = 1.0f; a.out0 = w.q; a.out1 = w.k; a.out2 = w.v;
-            a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N;
+            a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N; a.heads_tma = 1;
             if (h->tc_attn) { a.vt_which_plus1 = 3; a.vt_ld = N; }
             TPX_RC(gemm_linear(w.h16, D, l.Wqkv, S * N, 3 * D, D, EPI_HEADS, a, 0, st));
         }
@@ -544,6 +547,18 @@ int tpx_linear_heads(const void* A, int lda, const void* W, const void* bias, vo
     a.split_cols = split_cols; a.Dh = Dh; a.DhP = DhP; a.H = H; a.Nseq = n_seq_tokens;
     a.vt_which_plus1 = transposed_which >= 0 ? transposed_which + 1 : 0;
     a.vt_ld = transposed_ld;
+    if (Dh % 24 == 0 && n_seq_tokens % 32 == 0 && n_seq_tokens > 0 && M % n_seq_tokens == 0) {
+        // bulk-store epilogue: it writes the Dh real columns only, so the padding is cleared here (the DiT forward clears its
+        // workspace once per call instead)
+        void* outs[3] = {out0, out1, out2};
+        const size_t per = static_cast<size_t>(M / n_seq_tokens) * H * n_seq_tokens * DhP * 2;
+        for (int w = 0; w < N / split_cols && w < 3; ++w) {
+            TPX_CHECK(outs[w] != nullptr, TPX_ERR_ARG, "linear_heads: output %d is null", w);
+            const size_t bytes = w == transposed_which ? static_cast<size_t>(M / n_seq_tokens) * H * DhP * transposed_ld * 2 : per;
+            TPX_CUDA(cudaMemsetAsync(outs[w], 0, bytes, static_cast<cudaStream_t>(stream)));
+        }
+        a.heads_tma = 1;
+    }
     return gemm_linear(static_cast<const __half*>(A), lda, static_cast<const __half*>(W), M, N, K, EPI_HEADS, a, tile_n, static_cast<cudaStream_t>(stream));
 }
 

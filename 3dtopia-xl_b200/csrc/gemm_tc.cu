@@ -105,26 +105,28 @@ static CUtensorMapSwizzle swizzle_for(int bk) {
     return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-using MapKey = std::tuple<const void*, long long, long long, long long, int, int, int>;
+using MapKey = std::tuple<const void*, long long, long long, long long, int, int, int>;   // last: rank (2 / 5) * 16 + element bytes
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
-// 2-D: row-major [rows, K] fp16, box = [box_rows, bk]
-static int map_2d(const void* ptr, long long rows, long long K, long long ld, int box_rows, int bk, CUtensorMap* out) {
-    MapKey key{ptr, rows, K, ld, box_rows, bk, 2};
+// 2-D: row-major [rows, K] matrix of fp16 (esz 2) or fp32 (esz 4) elements, box = [box_rows, bk], swizzle = box row bytes (128/64/32)
+static int map_2d(const void* ptr, long long rows, long long K, long long ld, int box_rows, int bk, CUtensorMap* out, int esz = 2, bool swizzled = true) {
+    MapKey key{ptr, rows, K, ld, box_rows, bk, 2 * 16 + esz + (swizzled ? 0 : 8)};
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return TPX_OK; }
     EncodeTiledFn enc = encode_fn();
     TPX_CHECK(enc != nullptr, TPX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
-    TPX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, TPX_ERR_ARG, "TMA operand must be 16-B aligned (ptr %p ld %lld)", ptr, ld);
+    TPX_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0, TPX_ERR_ARG,
+              "TMA operand must be 16-B aligned (ptr %p, row stride %lld elements of %d bytes)", ptr, ld, esz);
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * esz};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzled ? swizzle_for(bk * esz / 2) : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TPX_CHECK(r == CUDA_SUCCESS, TPX_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (rows %lld K %lld ld %lld box %d x %d)", (int)r, rows, K, ld, box_rows, bk);
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps[key] = m;
@@ -134,7 +136,7 @@ static int map_2d(const void* ptr, long long rows, long long K, long long ld, in
 
 // 5-D: channels-last volume [P, S, S, S, C] fp16; box = 128 voxel rows x bk channels
 static int map_conv(const void* ptr, long long P, int S, int C, int bk, CUtensorMap* out) {
-    MapKey key{ptr, P, S, C, 0, bk, 5};
+    MapKey key{ptr, P, S, C, 0, bk, 5 * 16 + 2};
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return TPX_OK; }
@@ -160,7 +162,8 @@ int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long lon
 }
 
 template <int BN, int BK, int AMODE, int EPI>
-static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const CUtensorMap& te, const GemmArgs& a,
+                      cudaStream_t stream) {
     using Cfg = GemmCfg<BN, BK>;
     auto kern = gemm_tc_kernel<BN, BK, AMODE, EPI>;
     static bool attr_set = false;
@@ -170,7 +173,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
     }
     const int tiles = ((a.M + 127) / 128) * ((a.N + BN - 1) / BN);
     const int grid = tiles < gemm_num_sms() ? tiles : gemm_num_sms();
-    TPX_CUDA(launch_pdl(kern, dim3(grid), dim3(256), Cfg::SMEM_BYTES, stream, ta, tb, a));
+    TPX_CUDA(launch_pdl(kern, dim3(grid), dim3(256), Cfg::SMEM_BYTES, stream, ta, tb, tc, td, te, a));
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }
@@ -240,14 +243,47 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (rc != TPX_OK) return rc;
     rc = map_2d(p.W, p.N, p.K, p.K, p.BN, bk, &tb);
     if (rc != TPX_OK) return rc;
+    // output tensor map of the TMA epilogue: fp16 [M, N] in 64-column x 32-row boxes, or the fp32 residual in 32 x 32 boxes
+    CUtensorMap tc = ta, td = ta, te = ta;
+    if (p.epi == EPI_HEADS && a.heads_tma != 0) {
+        // 24-column bulk tensor stores of the head-split outputs (see epilogue_heads_tma); anything else takes the per-thread path
+        const bool ok = p.a_mode == AMODE_LINEAR && p.BN % 24 == 0 && p.N % p.BN == 0 && a.Dh % 24 == 0 && a.split_cols % 24 == 0 && a.Nseq % 32 == 0 &&
+                        a.Nseq > 0 && p.M % a.Nseq == 0 && a.DhP % 8 == 0 && (a.vt_which_plus1 == 0 || a.vt_ld % 8 == 0);
+        a.heads_tma = ok ? 1 : 0;
+        if (ok) {
+            const long long rows = static_cast<long long>(p.M / a.Nseq) * a.H * a.Nseq, rows_t = static_cast<long long>(p.M / a.Nseq) * a.H * a.DhP;
+            __half* outs[3] = {a.out0, a.out1, a.out2};
+            CUtensorMap* maps[3] = {&tc, &td, &te};
+            const int nwhich = p.N / a.split_cols;
+            for (int w = 0; w < nwhich && w < 3; ++w) {
+                TPX_CHECK(outs[w] != nullptr, TPX_ERR_ARG, "gemm: head-split output %d is null", w);
+                if (w + 1 == a.vt_which_plus1) rc = map_2d(outs[w], rows_t, a.vt_ld, a.vt_ld, 24, 32, maps[w], 2, false);
+                else rc = map_2d(outs[w], rows, a.DhP, a.DhP, 32, 24, maps[w], 2, false);
+                if (rc != TPX_OK) return rc;
+            }
+        }
+    } else {
+        a.heads_tma = 0;
+    }
+    if (gemm_tma_epilogue(p.epi, p.BN)) {
+        if (p.epi == EPI_GATED) {
+            TPX_CHECK(a.xres != nullptr && a.gate != nullptr, TPX_ERR_ARG, "gemm: gated epilogue without residual / gate");
+            rc = map_2d(a.xres, p.M, p.N, a.ldx, 32, 32, &tc, 4);
+        } else {
+            TPX_CHECK(a.out0 != nullptr && a.ldo >= p.N, TPX_ERR_ARG, "gemm: output pointer / row stride (%d < N %d)", a.ldo, p.N);
+            rc = map_2d(a.out0, p.M, p.N, a.ldo, 32, 64, &tc, 2);
+        }
+        if (rc != TPX_OK) return rc;
+    }
 
 #define TPX_CASE(BN_, BK_, AM_, EP_) \
-    if (p.BN == BN_ && bk == BK_ && p.a_mode == AM_ && p.epi == EP_) return launch_one<BN_, BK_, AM_, EP_>(ta, tb, a, stream);
+    if (p.BN == BN_ && bk == BK_ && p.a_mode == AM_ && p.epi == EP_) return launch_one<BN_, BK_, AM_, EP_>(ta, tb, tc, td, te, a, stream);
     // DiT (every tile width x every DiT epilogue, so any hidden size that is a multiple of 128 works)
     TPX_CASE(128, 64, AMODE_LINEAR, EPI_STORE)
     TPX_CASE(128, 64, AMODE_LINEAR, EPI_GELU)
     TPX_CASE(128, 64, AMODE_LINEAR, EPI_HEADS)
     TPX_CASE(128, 64, AMODE_LINEAR, EPI_GATED)
+    TPX_CASE(144, 64, AMODE_LINEAR, EPI_HEADS)      // two 72-wide heads per tile: the N = 1152 head projections in one wave
     TPX_CASE(192, 64, AMODE_LINEAR, EPI_STORE)
     TPX_CASE(192, 64, AMODE_LINEAR, EPI_GELU)
     TPX_CASE(192, 64, AMODE_LINEAR, EPI_HEADS)

@@ -45,6 +45,7 @@ struct GemmArgs {
     float alpha;
     float* out32;
     int n_valid, S3;
+    int heads_tma;    // EPI_HEADS: 1 = outputs leave as 24-column bulk tensor stores (launcher checked the geometry, padding is pre-zeroed)
     long long* dbg;   // timeline probe (tpx_debug_gemm_timeline): 16 int64 per CTA, nullptr in the product path
 };
 
@@ -55,10 +56,14 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias + gate tile, fp32*/;
+    // epilogue staging for the TMA stores: per epilogue warp two buffers of 32 rows x 128 B (1024-B aligned: 128-B swizzle)
+    static constexpr int STAGING_BYTES = (BN % 64 == 0 || BN % 24 == 0) ? 4 * 2 * 4096 : 0;
+    // dynamic shared memory is declared __align__(1024) (the kernel traps if the base is not), so no alignment slack is budgeted
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + 2048 /*bias + gate tile, fp32*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(B_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "stage operands must stay 1024-B aligned");
     static_assert(BN % 16 == 0 && BN <= 256, "UMMA N");
 };
@@ -95,6 +100,21 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
     const float e = __expf(2.0f * u);
     const float th = 1.0f - __fdividef(2.0f, 1.0f + e);
     return 0.5f * x * (1.0f + th);
+}
+
+// h(a), h(b) as floats through ONE packed conversion (F2FP.F16.F32.PACK_AB, ALU pipe); the scalar cvt.rn.f16.f32 is an XU-pipe
+// instruction (16 / clk / SM, shared with MUFU) and was the bound of the GELU / gated epilogues.
+__device__ __forceinline__ float2 round_h2(float a, float b) { return __half22float2(__floats2half2_rn(a, b)); }
+// gelu_tanh(x) = 0.5 x (1 + tanh(u)) = x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3):  x / (1 + 2^(-2 u log2 e)).
+// Five FMA-pipe operations + MUFU.EX2 + MUFU.RCP; saturates cleanly (2^+inf -> rcp(inf) = 0, 2^-inf -> 1).
+__device__ __forceinline__ float gelu_tanh_sigmoid(float x) {
+    const float k0 = -2.0f * 0.7978845608028654f * 1.4426950408889634f, k1 = k0 * 0.044715f;
+    const float t = x * x;
+    const float arg = x * fmaf(k1, t, k0);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
 }
 
 template <int EPI, int CH>
@@ -245,23 +265,210 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const float* __rest
     }
 }
 
+// ---- epilogue through shared memory + TMA (EPI_STORE / EPI_GELU / EPI_GATED, tiles that are a multiple of 64 wide) -----------
+// Each epilogue warp owns 32 accumulator rows (TMEM lanes) and walks the tile's columns in 32-column chunks; the tcgen05.ld of
+// chunk k+1 is in flight while chunk k is converted.  Results go to a 32-row x 128-B staging buffer in the 128-B-swizzled layout
+// (conflict-free 16-B stores) and leave as ONE bulk tensor store per 128-B row group:
+//   fp16 outputs: 64 columns per store (cp.async.bulk.tensor, full 128-B lines instead of 16-B pieces per thread);
+//   gated residual: 32 fp32 columns per cp.reduce.async.bulk.tensor .add — the L2 performs  x += h(gate * h(acc + b)),  so the
+//   epilogue never loads the residual (one add per element per launch: deterministic; the L2 adder flushes subnormals).
+// Rows >= M and columns >= N are clipped by the tensor map.
+constexpr bool gemm_tma_epilogue(int epi, int bn) { return (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_GATED) && bn % 64 == 0; }
+
+template <int EPI, int NCH>
+__device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMap* tmC, const float* __restrict__ sb, const float* __restrict__ sg,
+                                             bool gate_in_smem, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane) {
+    const uint32_t srow = stg + lane * 128;
+    const int sw = lane & 7;
+    uint32_t r[2][32];
+    tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        tmem_ld_wait_dep(r[k & 1]);
+        if (k + 1 < NCH) tmem_ld_32x32(taddr + (k + 1) * 32, r[(k + 1) & 1]);
+        const uint32_t* acc = r[k & 1];
+        const int c0 = k * 32;
+        if constexpr (EPI == EPI_GATED) {
+            if (lane == 0) bulk_wait_read<1>();     // the reduce issued two chunks ago has read this buffer
+            __syncwarp();
+            const uint32_t dst = srow + (sbuf & 1) * 4096;
+            float gt[32];
+            if (gate_in_smem) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + i);
+                    gt[i] = g4.x; gt[i + 1] = g4.y; gt[i + 2] = g4.z; gt[i + 3] = g4.w;
+                }
+            } else {
+                const int b = ((row0 + lane) / g.rows_per_batch) % g.gate_batches;
+                const __half* gp = g.gate + static_cast<size_t>(b) * g.gate_bstride + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Pack8 t;
+                    t.u = (n0 + c0 + j * 8 < g.N) ? *reinterpret_cast<const uint4*>(gp + j * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gt[j * 8 + i] = __half2float(t.h[i]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j * 4);
+                const float2 v01 = round_h2(__uint_as_float(acc[j * 4 + 0]) + b4.x, __uint_as_float(acc[j * 4 + 1]) + b4.y);
+                const float2 v23 = round_h2(__uint_as_float(acc[j * 4 + 2]) + b4.z, __uint_as_float(acc[j * 4 + 3]) + b4.w);
+                const float2 o01 = round_h2(gt[j * 4 + 0] * v01.x, gt[j * 4 + 1] * v01.y);
+                const float2 o23 = round_h2(gt[j * 4 + 2] * v23.x, gt[j * 4 + 3] * v23.y);
+                const float o[4] = {o01.x, o01.y, o23.x, o23.y};
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ sw) << 4)), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_reduce_add_2d(tmC, stg + (sbuf & 1) * 4096, n0 + c0, row0);
+                bulk_commit();
+            }
+            ++sbuf;
+        } else {
+            if ((k & 1) == 0) {
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+            }
+            const uint32_t dst = srow + (sbuf & 1) * 4096;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+                float x[4] = {__uint_as_float(acc[i]) + b4.x, __uint_as_float(acc[i + 1]) + b4.y, __uint_as_float(acc[i + 2]) + b4.z,
+                              __uint_as_float(acc[i + 3]) + b4.w};
+                if (EPI == EPI_GELU || g.post_scale != 1.0f) {     // otherwise the pack below is the one rounding
+                    const float2 r01 = round_h2(x[0], x[1]), r23 = round_h2(x[2], x[3]);
+                    x[0] = r01.x; x[1] = r01.y; x[2] = r23.x; x[3] = r23.y;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if constexpr (EPI == EPI_GELU) x[e] = gelu_tanh_sigmoid(x[e]);
+                        else x[e] *= g.post_scale;
+                    }
+                }
+                const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+                pk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((k & 1) * 4 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                             "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                             : "memory");
+            if ((k & 1) == 1) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tmC, stg + (sbuf & 1) * 4096, n0 + (k - 1) * 32, row0);
+                    bulk_commit();
+                }
+                ++sbuf;
+            }
+        }
+    }
+}
+
+// ---- EPI_HEADS through shared memory + TMA ---------------------------------------------------------------------------------------
+// Column groups of 24 (= Dh / 3 for Dh = 72; every tile, head and q/k/v boundary is a multiple of 24): a warp's 32 rows x 24
+// columns are one box of the destination [B*H*Nseq, DhP] matrix (rows (b, head, n0 .. n0+31), columns d0 .. d0+23), or — for the
+// transposed V the tcgen05 attention reads — one 24-row x 32-token box of [B*H*DhP, vt_ld].  Needs Nseq % 32 == 0 (a 32-row slab
+// never straddles a sequence), Dh % 24 == 0, and the head-dim padding columns d >= Dh already zero (the launcher's caller memsets).
+constexpr int HG = 24;
+template <int NG>
+__device__ __forceinline__ void epilogue_heads_tma(const GemmArgs& g, const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
+                                                   const float* __restrict__ sb, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane) {
+    if (row0 >= g.M) return;                        // whole slab outside the matrix (M is a multiple of 32 here)
+    const int b = row0 / g.Nseq, nfirst = row0 - b * g.Nseq;
+    int which = n0 / g.split_cols;
+    int c = n0 - which * g.split_cols;
+    int head = c / g.Dh;
+    int d0 = c - head * g.Dh;
+    uint32_t r[2][24];
+    tmem_ld_32x16_to(taddr, r[0]);
+    tmem_ld_32x8_to(taddr + 16, r[0] + 16);
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        tmem_ld_wait_dep24(r[k & 1]);
+        if (k + 1 < NG) {
+            tmem_ld_32x16_to(taddr + (k + 1) * HG, r[(k + 1) & 1]);
+            tmem_ld_32x8_to(taddr + (k + 1) * HG + 16, r[(k + 1) & 1] + 16);
+        }
+        const uint32_t* acc = r[k & 1];
+        const int c0 = k * HG;
+        const bool sc = g.post_scale != 1.0f && which == 0;
+        uint32_t pk[12];
+#pragma unroll
+        for (int i = 0; i < HG; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+            float x[4] = {__uint_as_float(acc[i]) + b4.x, __uint_as_float(acc[i + 1]) + b4.y, __uint_as_float(acc[i + 2]) + b4.z,
+                          __uint_as_float(acc[i + 3]) + b4.w};
+            if (sc) {
+                const float2 r01 = round_h2(x[0], x[1]), r23 = round_h2(x[2], x[3]);
+                x[0] = r01.x * g.post_scale; x[1] = r01.y * g.post_scale; x[2] = r23.x * g.post_scale; x[3] = r23.y * g.post_scale;
+            }
+            const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+            pk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t buf = stg + (sbuf & 1) * 4096;
+        const bool transposed = which + 1 == g.vt_which_plus1;
+        if (transposed) {
+            // staging [24 d][32 tokens] fp16: lane = token
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const uint16_t lo = static_cast<uint16_t>(pk[i] & 0xFFFFu), hi = static_cast<uint16_t>(pk[i] >> 16);
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(buf + (2 * i) * 64 + lane * 2), "h"(lo) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(buf + (2 * i + 1) * 64 + lane * 2), "h"(hi) : "memory");
+            }
+        } else {
+            // staging [32 rows][24 columns] fp16 (48-B rows: conflict-free 16-B stores)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 48 + q * 16), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
+                             "r"(pk[4 * q + 3])
+                             : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            if (transposed) tma_store_2d(tmV, buf, nfirst, (b * g.H + head) * g.DhP + d0);
+            else tma_store_2d(which == 0 ? tmQ : (which == 1 ? tmK : tmV), buf, d0, (b * g.H + head) * g.Nseq + nfirst);
+            bulk_commit();
+        }
+        ++sbuf;
+        d0 += HG;
+        if (d0 >= g.Dh) {
+            d0 = 0;
+            if (++head == g.H) { head = 0; ++which; }
+        }
+    }
+}
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int BK, int AMODE, int EPI>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmE, const GemmArgs g) {
     using Cfg = GemmCfg<BN, BK>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
-    // access to generic LD/ST instead of LDS/STS)
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    constexpr bool kTmaEpi = gemm_tma_epilogue(EPI, BN);
+    constexpr bool kHeadsTma = EPI == EPI_HEADS && BN % HG == 0 && Cfg::STAGING_BYTES > 0;   // taken when g.heads_tma is set
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the swizzled operand / staging tiles need a 1024-B aligned base
+    // layout: [operand ring][epilogue staging][barriers 256 B][bias + gate tile 2 KB]
+    constexpr int OFF_BAR = STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BAR + 256);
     float* s_gate = s_bias + 256;
 
     const int warp = threadIdx.x >> 5;
@@ -270,6 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if constexpr (kTmaEpi) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -385,6 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         const bool gate_in_smem = (EPI == EPI_GATED) && (g.rows_per_batch % 128 == 0);
         long long w_tfull = 0, t_proc = 0;
+        uint32_t sbuf = 0;      // running staging-buffer index of this warp (two buffers in rotation)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             const int n0 = n_blk * BN;
@@ -420,19 +629,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             w_tfull += tp - tw;
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
-            constexpr int CH = BN >= 32 ? 32 : 16;
+            bool done = false;
+            if constexpr (kHeadsTma) {
+                if (g.heads_tma != 0) {
+                    epilogue_heads_tma<BN / HG>(g, &tmC, &tmD, &tmE, s_bias, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192, sbuf,
+                                                m_blk * 128 + quad * 32, n0, lane);
+                    done = true;
+                }
+            }
+            if constexpr (kTmaEpi) {
+                epilogue_tma<EPI, BN / 32>(g, &tmC, s_bias, s_gate, gate_in_smem, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192, sbuf,
+                                           m_blk * 128 + quad * 32, n0, lane);
+            } else if (!done) {
+                constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH) {
-                uint32_t r[32];
-                if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, r);
-                else tmem_ld_32x16(taddr + c0, r);
-                tmem_ld_wait();
-                epi_chunk<EPI, CH>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
+                for (int c0 = 0; c0 < BN; c0 += CH) {
+                    uint32_t r[32];
+                    if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, r);
+                    else tmem_ld_32x16(taddr + c0, r);
+                    tmem_ld_wait();
+                    epi_chunk<EPI, CH>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
             if (dbg != nullptr) t_proc += clock64() - tp;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if constexpr (kTmaEpi || kHeadsTma) {
+            if (lane == 0) bulk_wait<0>();          // every bulk store / reduce of this warp has been performed
         }
         if (dbg != nullptr && et == 0) { dbg[7] = w_tfull; dbg[8] = t_proc; dbg[9] = clock64(); }
     }

@@ -69,8 +69,27 @@ def test_linear_gated_residual():
     assert (x - ref).abs().max() < 2e-2 and rel_l2(x, ref) < 1e-3
 
 
-def test_linear_heads_transposed_v():
-    """V stored as [b, head, DhP, tokens] for the tcgen05 attention's PV operand; zero rows for d >= Dh."""
+def test_linear_gated_ragged_rows_and_per_row_gate():
+    """Sequence length that is not a multiple of the 128-row tile: the gate is looked up per row, the last tile is partial,
+    and two launches accumulate (the residual update is an L2-side add)."""
+    B, N, D, K = 3, 200, 256, 128
+    A, W, b = _rand(B * N, K, seed=51), _rand(D, K, scale=1 / 11, seed=52), _rand(D, seed=53)
+    gate = _rand(B, D, seed=54)
+    x = torch.randn(B * N, D, device="cuda")
+    x0 = x.clone()
+    for _ in range(2):
+        _lib.check(_lib.lib().tpx_linear_gated(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), gate.data_ptr(), D, B, N, x.data_ptr(), D, B * N, D, K, 0, st()))
+    upd = (gate.float().repeat_interleave(N, 0) * linear_ref(A, W, b).float()).half().float()
+    ref = (x0 + upd) + upd
+    torch.cuda.synchronize()
+    # (one fp16 ulp where the tensor core's fp32 summation order rounds acc+bias the other way than torch's)
+    assert rel_l2(x, ref) < 1e-3 and (x - ref).abs().max() < 4e-2, float((x - ref).abs().max())
+
+
+@pytest.mark.parametrize("tile", [0, 144, 192])
+def test_linear_heads_transposed_v(tile):
+    """V stored as [b, head, DhP, tokens] for the tcgen05 attention's PV operand; zero rows for d >= Dh.  Tiles 144 / 192 take
+    the bulk-tensor-store epilogue (24-column groups), 0 picks a width that takes the per-thread one."""
     B, N, H, Dh, DhP, K = 2, 256, 16, 72, 80, 256
     D = H * Dh
     A, W, b = _rand(B * N, K, seed=18), _rand(3 * D, K, scale=1 / 16, seed=19), _rand(3 * D, seed=20)
@@ -78,12 +97,28 @@ def test_linear_heads_transposed_v():
     k = torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda")
     vT = torch.full((B, H, DhP, N), 7.0, dtype=torch.float16, device="cuda")
     _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), q.data_ptr(), k.data_ptr(), vT.data_ptr(),
-                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, 0, 2, N, st()))
+                                           B * N, 3 * D, K, D, H, Dh, DhP, N, 1.0, tile, 2, N, st()))
     ref = linear_ref(A, W, b).reshape(B, N, 3, H, Dh)
     torch.cuda.synchronize()
-    assert torch.all(vT[:, :, Dh:, :] == 0) and torch.all(k[..., Dh:] == 0)
+    assert torch.all(vT[:, :, Dh:, :] == 0) and torch.all(k[..., Dh:] == 0) and torch.all(q[..., Dh:] == 0)
     assert rel_l2(vT[:, :, :Dh, :], ref[:, :, 2].permute(0, 2, 3, 1)) < 2e-3
     assert rel_l2(q[..., :Dh], ref[:, :, 0].permute(0, 2, 1, 3)) < 2e-3
+    assert rel_l2(k[..., :Dh], ref[:, :, 1].permute(0, 2, 1, 3)) < 2e-3
+
+
+def test_linear_heads_bulk_store_q_scaled():
+    """The N = 1152 head projection as the DiT issues it (144-wide tiles, post-scale re-rounding of q, M = 2 sequences)."""
+    B, N, H, Dh, DhP, K = 2, 384, 16, 72, 80, 1152
+    D = H * Dh
+    A, W, b = _rand(B * N, K, seed=61), _rand(D, K, scale=K ** -0.5, seed=62), _rand(D, seed=63)
+    q = torch.full((B, H, N, DhP), 7.0, dtype=torch.float16, device="cuda")
+    s = Dh ** -0.5
+    _lib.check(_lib.lib().tpx_linear_heads(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), q.data_ptr(), None, None, B * N, D, K, D, H, Dh, DhP, N, s, 144, -1, 0,
+                                           st()))
+    ref = linear_ref(A, W, b, post_scale=s).reshape(B, N, H, Dh)
+    torch.cuda.synchronize()
+    assert torch.all(q[..., Dh:] == 0)
+    assert rel_l2(q[..., :Dh], ref.permute(0, 2, 1, 3)) < 2e-3
 
 
 @pytest.mark.parametrize("M,N,K,tile", [(256, 128, 64, -128), (512, 256, 256, -256), (4096, 1152, 1152, -128), (4096, 3456, 1152, -192), (4096, 4608, 1152, -256),
