@@ -195,9 +195,18 @@ int pick_bn_2cta(int M, int N) {
     return best;
 }
 
-bool use_2cta() {
-    static const int v = getenv("TPX_GEMM_2CTA") ? atoi(getenv("TPX_GEMM_2CTA")) : 0;   // opt-in (TPX_GEMM_2CTA=1): see the note in gemm_tc2_kernel
-    return v != 0;
+// TPX_GEMM_2CTA: unset / "auto" = the cta_group::2 kernel where it measured faster (long-K or very wide linears: fc1, fc2);
+// 0 = never, 1 = every linear with M >= 256.
+int mode_2cta() {
+    static const int v = getenv("TPX_GEMM_2CTA") ? (getenv("TPX_GEMM_2CTA")[0] == 'a' ? 2 : atoi(getenv("TPX_GEMM_2CTA"))) : 2;
+    return v;
+}
+bool use_2cta() { return mode_2cta() == 1; }
+bool want_2cta(int M, int N, int K, int epi) {
+    const int m = mode_2cta();
+    if (m == 0 || M < 256) return false;
+    if (m == 1) return true;
+    return M >= 1024 && (K >= 2304 || N >= 4096) && epi != EPI_HEADS;
 }
 
 // tile_n: 0 = automatic; > 0 = 1-CTA kernel with that tile width; < 0 = 2-CTA (cta_group::2) kernel with width -tile_n
@@ -205,7 +214,7 @@ int gemm_linear(const __half* A, int lda, const __half* W, int M, int N, int K, 
     GemmProblem p{};
     p.A = A; p.a_mode = AMODE_LINEAR; p.lda = lda; p.W = W; p.M = M; p.N = N; p.K = K;
     p.epi = epi; p.args = args;
-    if (tile_n < 0 || (tile_n == 0 && use_2cta() && M >= 256)) {
+    if (tile_n < 0 || (tile_n == 0 && want_2cta(M, N, K, epi))) {
         p.BN = tile_n < 0 ? -tile_n : pick_bn_2cta(M, N);
         return launch_gemm_2cta(p, st);
     }
@@ -424,7 +433,7 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
             GemmArgs a{};
             a.bias = l.bq; a.post_scale = qscale; a.out0 = w.q;
             a.split_cols = D; a.Dh = h->Dh; a.DhP = h->DhP; a.H = h->H; a.Nseq = N; a.heads_tma = 1;
-            TPX_RC(gemm_linear(w.h16, D, l.Wq, Sc * N, D, D, EPI_HEADS, a, D % 144 == 0 && h->Dh % 24 == 0 ? 144 : 0, st));
+            TPX_RC(gemm_linear(w.h16, D, l.Wq, Sc * N, D, D, EPI_HEADS, a, D % 144 == 0 && h->Dh % 24 == 0 && N % 32 == 0 ? (use_2cta() ? -144 : 144) : 0, st));
         }
         if (h->tc_attn) TPX_RC(launch_attention_tc(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_v, w.ao, Sc, h->H, N, M, h->cond_MP, h->Dh, qscale, st));
         else TPX_RC(launch_attention(w.q, h->ck + i * per_layer_kv, h->cv + i * per_layer_kv, w.ao, Sc, h->H, N, M, h->Dh, h->DhP, qscale, st));

@@ -161,6 +161,43 @@ int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long lon
     return map_2d(ptr, rows, cols, ld, box_rows, box_cols, out);
 }
 
+// Output tensor maps of the bulk-store epilogues (tc / td / te default to copies of the A map when unused).  Validates the geometry the
+// 24-column head-split stores need and clears a.heads_tma when it does not hold (the kernel then takes the per-thread path).
+static int make_output_maps(const GemmProblem& p, GemmArgs& a, const CUtensorMap& ta, CUtensorMap& tc, CUtensorMap& td, CUtensorMap& te) {
+    int rc = TPX_OK;
+    tc = ta; td = ta; te = ta;
+    if (p.epi == EPI_HEADS && a.heads_tma != 0) {
+        const bool ok = p.a_mode == AMODE_LINEAR && p.BN % 24 == 0 && p.N % p.BN == 0 && a.Dh % 24 == 0 && a.split_cols % 24 == 0 && a.Nseq % 32 == 0 &&
+                        a.Nseq > 0 && p.M % a.Nseq == 0 && a.DhP % 8 == 0 && (a.vt_which_plus1 == 0 || a.vt_ld % 8 == 0);
+        a.heads_tma = ok ? 1 : 0;
+        if (ok) {
+            const long long rows = static_cast<long long>(p.M / a.Nseq) * a.H * a.Nseq, rows_t = static_cast<long long>(p.M / a.Nseq) * a.H * a.DhP;
+            __half* outs[3] = {a.out0, a.out1, a.out2};
+            CUtensorMap* maps[3] = {&tc, &td, &te};
+            const int nwhich = p.N / a.split_cols;
+            for (int w = 0; w < nwhich && w < 3; ++w) {
+                TPX_CHECK(outs[w] != nullptr, TPX_ERR_ARG, "gemm: head-split output %d is null", w);
+                if (w + 1 == a.vt_which_plus1) rc = map_2d(outs[w], rows_t, a.vt_ld, a.vt_ld, 24, 32, maps[w], 2, false);
+                else rc = map_2d(outs[w], rows, a.DhP, a.DhP, 32, 24, maps[w], 2, false);
+                if (rc != TPX_OK) return rc;
+            }
+        }
+    } else {
+        a.heads_tma = 0;
+    }
+    if (gemm_tma_epilogue(p.epi, p.BN)) {
+        // fp16 [M, N] in 64-column x 32-row boxes, or the fp32 residual in 32 x 32 boxes
+        if (p.epi == EPI_GATED) {
+            TPX_CHECK(a.xres != nullptr && a.gate != nullptr, TPX_ERR_ARG, "gemm: gated epilogue without residual / gate");
+            rc = map_2d(a.xres, p.M, p.N, a.ldx, 32, 32, &tc, 4);
+        } else {
+            TPX_CHECK(a.out0 != nullptr && a.ldo >= p.N, TPX_ERR_ARG, "gemm: output pointer / row stride (%d < N %d)", a.ldo, p.N);
+            rc = map_2d(a.out0, p.M, p.N, a.ldo, 32, 64, &tc, 2);
+        }
+    }
+    return rc;
+}
+
 template <int BN, int BK, int AMODE, int EPI>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const CUtensorMap& te, const GemmArgs& a,
                       cudaStream_t stream) {
@@ -179,7 +216,8 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 }
 
 template <int BN, int EPI>
-static int launch_one_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+static int launch_one_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const CUtensorMap& te, GemmArgs a,
+                           cudaStream_t stream) {
     using Cfg = Gemm2Cfg<BN>;
     auto kern = gemm_tc2_kernel<BN, EPI>;
     static bool attr_set = false;
@@ -190,7 +228,14 @@ static int launch_one_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const G
     const int tiles = ((a.M + 255) / 256) * ((a.N + BN - 1) / BN);
     const int pairs = gemm_num_sms() / 2;
     const int clusters = tiles < pairs ? tiles : pairs;
-    kern<<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);   // plain launch (cluster dims compiled in); see the note in the kernel
+    // TPX_2CTA_PDL: 0 = plain stream-serialised launch; 1 = programmatic dependent launch, trigger at exit; 2 = PDL with the early trigger
+    static const int pdl_mode = getenv("TPX_2CTA_PDL") ? atoi(getenv("TPX_2CTA_PDL")) : 2;
+    a.pdl_trigger = pdl_mode >= 2 ? 1 : 0;
+    if (pdl_mode >= 1) {
+        TPX_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, td, te, a));
+    } else {
+        kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, td, te, a);   // cluster dims are compiled in
+    }
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }
@@ -203,14 +248,19 @@ int launch_gemm_2cta(const GemmProblem& p, cudaStream_t stream) {
     a.M = p.M;
     a.N = p.N;
     a.num_kb = (p.K + 63) / 64;
-    CUtensorMap ta, tb;
+    a.dbg = g_gemm_dbg;
+    CUtensorMap ta, tb, tc, td, te;
     int rc = map_2d(p.A, p.M, p.K, p.lda, 128, 64, &ta);
     if (rc != TPX_OK) return rc;
     rc = map_2d(p.W, p.N, p.K, p.K, p.BN / 2, 64, &tb);
     if (rc != TPX_OK) return rc;
+    rc = make_output_maps(p, a, ta, tc, td, te);
+    if (rc != TPX_OK) return rc;
+    TPX_CHECK(p.BN != 144 || a.heads_tma != 0, TPX_ERR_SHAPE, "gemm_2cta: the 144-wide tile exists for the bulk-store head split only");
 #define TPX_CASE2(BN_, EP_) \
-    if (p.BN == BN_ && p.epi == EP_) return launch_one_2cta<BN_, EP_>(ta, tb, a, stream);
+    if (p.BN == BN_ && p.epi == EP_) return launch_one_2cta<BN_, EP_>(ta, tb, tc, td, te, a, stream);
     TPX_CASE2(128, EPI_STORE) TPX_CASE2(128, EPI_GELU) TPX_CASE2(128, EPI_HEADS) TPX_CASE2(128, EPI_GATED)
+    TPX_CASE2(144, EPI_HEADS)
     TPX_CASE2(192, EPI_STORE) TPX_CASE2(192, EPI_GELU) TPX_CASE2(192, EPI_HEADS) TPX_CASE2(192, EPI_GATED)
     TPX_CASE2(256, EPI_STORE) TPX_CASE2(256, EPI_GELU) TPX_CASE2(256, EPI_HEADS) TPX_CASE2(256, EPI_GATED)
 #undef TPX_CASE2
@@ -243,38 +293,10 @@ int launch_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (rc != TPX_OK) return rc;
     rc = map_2d(p.W, p.N, p.K, p.K, p.BN, bk, &tb);
     if (rc != TPX_OK) return rc;
-    // output tensor map of the TMA epilogue: fp16 [M, N] in 64-column x 32-row boxes, or the fp32 residual in 32 x 32 boxes
-    CUtensorMap tc = ta, td = ta, te = ta;
-    if (p.epi == EPI_HEADS && a.heads_tma != 0) {
-        // 24-column bulk tensor stores of the head-split outputs (see epilogue_heads_tma); anything else takes the per-thread path
-        const bool ok = p.a_mode == AMODE_LINEAR && p.BN % 24 == 0 && p.N % p.BN == 0 && a.Dh % 24 == 0 && a.split_cols % 24 == 0 && a.Nseq % 32 == 0 &&
-                        a.Nseq > 0 && p.M % a.Nseq == 0 && a.DhP % 8 == 0 && (a.vt_which_plus1 == 0 || a.vt_ld % 8 == 0);
-        a.heads_tma = ok ? 1 : 0;
-        if (ok) {
-            const long long rows = static_cast<long long>(p.M / a.Nseq) * a.H * a.Nseq, rows_t = static_cast<long long>(p.M / a.Nseq) * a.H * a.DhP;
-            __half* outs[3] = {a.out0, a.out1, a.out2};
-            CUtensorMap* maps[3] = {&tc, &td, &te};
-            const int nwhich = p.N / a.split_cols;
-            for (int w = 0; w < nwhich && w < 3; ++w) {
-                TPX_CHECK(outs[w] != nullptr, TPX_ERR_ARG, "gemm: head-split output %d is null", w);
-                if (w + 1 == a.vt_which_plus1) rc = map_2d(outs[w], rows_t, a.vt_ld, a.vt_ld, 24, 32, maps[w], 2, false);
-                else rc = map_2d(outs[w], rows, a.DhP, a.DhP, 32, 24, maps[w], 2, false);
-                if (rc != TPX_OK) return rc;
-            }
-        }
-    } else {
-        a.heads_tma = 0;
-    }
-    if (gemm_tma_epilogue(p.epi, p.BN)) {
-        if (p.epi == EPI_GATED) {
-            TPX_CHECK(a.xres != nullptr && a.gate != nullptr, TPX_ERR_ARG, "gemm: gated epilogue without residual / gate");
-            rc = map_2d(a.xres, p.M, p.N, a.ldx, 32, 32, &tc, 4);
-        } else {
-            TPX_CHECK(a.out0 != nullptr && a.ldo >= p.N, TPX_ERR_ARG, "gemm: output pointer / row stride (%d < N %d)", a.ldo, p.N);
-            rc = map_2d(a.out0, p.M, p.N, a.ldo, 32, 64, &tc, 2);
-        }
-        if (rc != TPX_OK) return rc;
-    }
+    CUtensorMap tc, td, te;
+    rc = make_output_maps(p, a, ta, tc, td, te);
+    if (rc != TPX_OK) return rc;
+    TPX_CHECK(p.BN != 144 || a.heads_tma != 0, TPX_ERR_SHAPE, "gemm: the 144-wide tile exists for the bulk-store head split only");
 
 #define TPX_CASE(BN_, BK_, AM_, EP_) \
     if (p.BN == BN_ && bk == BK_ && p.a_mode == AM_ && p.epi == EP_) return launch_one<BN_, BK_, AM_, EP_>(ta, tb, tc, td, te, a, stream);

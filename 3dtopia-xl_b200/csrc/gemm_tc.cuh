@@ -45,6 +45,7 @@ struct GemmArgs {
     float alpha;
     float* out32;
     int n_valid, S3;
+    int pdl_trigger;  // 2-CTA kernel: 1 = griddepcontrol.launch_dependents after the prologue (launched with the PDL attribute)
     int heads_tma;    // EPI_HEADS: 1 = outputs leave as 24-column bulk tensor stores (launcher checked the geometry, padding is pre-zeroed)
     long long* dbg;   // timeline probe (tpx_debug_gemm_timeline): 16 int64 per CTA, nullptr in the product path
 };
@@ -275,23 +276,38 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const float* __rest
 // Rows >= M and columns >= N are clipped by the tensor map.
 constexpr bool gemm_tma_epilogue(int epi, int bn) { return (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_GATED) && bn % 64 == 0; }
 
-template <int EPI, int NCH>
+// NSPLIT warps share one 32-row slab (the 2-CTA kernel runs 8 epilogue warps: NSPLIT = 2, this warp is `part`); a warp owns NBUF
+// staging buffers of 4 KB.
+template <int NBUF>
+__device__ __forceinline__ void staging_acquire(int lane) {
+    if (lane == 0) bulk_wait_read<NBUF - 1>();      // the bulk operation that last read the buffer about to be rewritten is done
+    __syncwarp();
+}
+
+template <int EPI, int NCH, int NSPLIT, int NBUF>
 __device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMap* tmC, const float* __restrict__ sb, const float* __restrict__ sg,
-                                             bool gate_in_smem, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane) {
+                                             bool gate_in_smem, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane, int part) {
     const uint32_t srow = stg + lane * 128;
     const int sw = lane & 7;
+    // this warp's chunks: units of UW chunks (fp16: 2 chunks = one 128-B row of 64 columns; gated: 1 chunk = 32 fp32 columns)
+    constexpr int UW = EPI == EPI_GATED ? 1 : 2;
+    constexpr int NU = NCH / UW;
+    constexpr int NIT = ((NU + NSPLIT - 1) / NSPLIT) * UW;      // chunk iterations of one warp (some may fall outside the tile)
+    auto chunk_of = [&](int it) { return ((it / UW) * NSPLIT + part) * UW + (it % UW); };
     uint32_t r[2][32];
-    tmem_ld_32x32(taddr, r[0]);
+    if (chunk_of(0) < NCH) tmem_ld_32x32(taddr + chunk_of(0) * 32, r[0]);
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-        tmem_ld_wait_dep(r[k & 1]);
-        if (k + 1 < NCH) tmem_ld_32x32(taddr + (k + 1) * 32, r[(k + 1) & 1]);
-        const uint32_t* acc = r[k & 1];
+    for (int it = 0; it < NIT; ++it) {
+        const int k = chunk_of(it);
+        if (k >= NCH) break;                        // warp-uniform
+        tmem_ld_wait_dep(r[it & 1]);
+        if (it + 1 < NIT && chunk_of(it + 1) < NCH) tmem_ld_32x32(taddr + chunk_of(it + 1) * 32, r[(it + 1) & 1]);
+        const uint32_t* acc = r[it & 1];
         const int c0 = k * 32;
         if constexpr (EPI == EPI_GATED) {
-            if (lane == 0) bulk_wait_read<1>();     // the reduce issued two chunks ago has read this buffer
-            __syncwarp();
-            const uint32_t dst = srow + (sbuf & 1) * 4096;
+            staging_acquire<NBUF>(lane);
+            const uint32_t boff = NBUF == 1 ? 0u : (sbuf & 1) * 4096u;
+            const uint32_t dst = srow + boff;
             float gt[32];
             if (gate_in_smem) {
 #pragma unroll
@@ -323,16 +339,14 @@ __device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMa
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_reduce_add_2d(tmC, stg + (sbuf & 1) * 4096, n0 + c0, row0);
+                tma_reduce_add_2d(tmC, stg + boff, n0 + c0, row0);
                 bulk_commit();
             }
             ++sbuf;
         } else {
-            if ((k & 1) == 0) {
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
-            }
-            const uint32_t dst = srow + (sbuf & 1) * 4096;
+            if ((it & 1) == 0) staging_acquire<NBUF>(lane);
+            const uint32_t boff = NBUF == 1 ? 0u : (sbuf & 1) * 4096u;
+            const uint32_t dst = srow + boff;
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -354,14 +368,14 @@ __device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMa
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((k & 1) * 4 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((it & 1) * 4 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
                              "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                              : "memory");
-            if ((k & 1) == 1) {
+            if ((it & 1) == 1) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(tmC, stg + (sbuf & 1) * 4096, n0 + (k - 1) * 32, row0);
+                    tma_store_2d(tmC, stg + boff, n0 + (k - 1) * 32, row0);
                     bulk_commit();
                 }
                 ++sbuf;
@@ -376,27 +390,34 @@ __device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMa
 // transposed V the tcgen05 attention reads — one 24-row x 32-token box of [B*H*DhP, vt_ld].  Needs Nseq % 32 == 0 (a 32-row slab
 // never straddles a sequence), Dh % 24 == 0, and the head-dim padding columns d >= Dh already zero (the launcher's caller memsets).
 constexpr int HG = 24;
-template <int NG>
+template <int NG, int NSPLIT, int NBUF>
 __device__ __forceinline__ void epilogue_heads_tma(const GemmArgs& g, const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
-                                                   const float* __restrict__ sb, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane) {
+                                                   const float* __restrict__ sb, uint32_t taddr, uint32_t stg, uint32_t& sbuf, int row0, int n0, int lane,
+                                                   int part) {
     if (row0 >= g.M) return;                        // whole slab outside the matrix (M is a multiple of 32 here)
     const int b = row0 / g.Nseq, nfirst = row0 - b * g.Nseq;
-    int which = n0 / g.split_cols;
-    int c = n0 - which * g.split_cols;
-    int head = c / g.Dh;
-    int d0 = c - head * g.Dh;
+    constexpr int NIT = (NG + NSPLIT - 1) / NSPLIT;
     uint32_t r[2][24];
-    tmem_ld_32x16_to(taddr, r[0]);
-    tmem_ld_32x8_to(taddr + 16, r[0] + 16);
+    if (part < NG) {
+        tmem_ld_32x16_to(taddr + part * HG, r[0]);
+        tmem_ld_32x8_to(taddr + part * HG + 16, r[0] + 16);
+    }
 #pragma unroll
-    for (int k = 0; k < NG; ++k) {
-        tmem_ld_wait_dep24(r[k & 1]);
-        if (k + 1 < NG) {
-            tmem_ld_32x16_to(taddr + (k + 1) * HG, r[(k + 1) & 1]);
-            tmem_ld_32x8_to(taddr + (k + 1) * HG + 16, r[(k + 1) & 1] + 16);
+    for (int it = 0; it < NIT; ++it) {
+        const int k = it * NSPLIT + part;
+        if (k >= NG) break;                         // warp-uniform
+        tmem_ld_wait_dep24(r[it & 1]);
+        if (it + 1 < NIT && k + NSPLIT < NG) {
+            tmem_ld_32x16_to(taddr + (k + NSPLIT) * HG, r[(it + 1) & 1]);
+            tmem_ld_32x8_to(taddr + (k + NSPLIT) * HG + 16, r[(it + 1) & 1] + 16);
         }
-        const uint32_t* acc = r[k & 1];
+        const uint32_t* acc = r[it & 1];
         const int c0 = k * HG;
+        const int col = n0 + c0;
+        const int which = col / g.split_cols;
+        const int cw = col - which * g.split_cols;
+        const int head = cw / g.Dh;
+        const int d0 = cw - head * g.Dh;
         const bool sc = g.post_scale != 1.0f && which == 0;
         uint32_t pk[12];
 #pragma unroll
@@ -412,9 +433,8 @@ __device__ __forceinline__ void epilogue_heads_tma(const GemmArgs& g, const CUte
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
             pk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-        const uint32_t buf = stg + (sbuf & 1) * 4096;
+        staging_acquire<NBUF>(lane);
+        const uint32_t buf = stg + (NBUF == 1 ? 0u : (sbuf & 1) * 4096u);
         const bool transposed = which + 1 == g.vt_which_plus1;
         if (transposed) {
             // staging [24 d][32 tokens] fp16: lane = token
@@ -440,11 +460,6 @@ __device__ __forceinline__ void epilogue_heads_tma(const GemmArgs& g, const CUte
             bulk_commit();
         }
         ++sbuf;
-        d0 += HG;
-        if (d0 >= g.Dh) {
-            d0 = 0;
-            if (++head == g.H) { head = 0; ++which; }
-        }
     }
 }
 
@@ -632,14 +647,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bool done = false;
             if constexpr (kHeadsTma) {
                 if (g.heads_tma != 0) {
-                    epilogue_heads_tma<BN / HG>(g, &tmC, &tmD, &tmE, s_bias, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192, sbuf,
-                                                m_blk * 128 + quad * 32, n0, lane);
+                    epilogue_heads_tma<BN / HG, 1, 2>(g, &tmC, &tmD, &tmE, s_bias, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192, sbuf,
+                                                      m_blk * 128 + quad * 32, n0, lane, 0);
                     done = true;
                 }
             }
             if constexpr (kTmaEpi) {
-                epilogue_tma<EPI, BN / 32>(g, &tmC, s_bias, s_gate, gate_in_smem, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192, sbuf,
-                                           m_blk * 128 + quad * 32, n0, lane);
+                epilogue_tma<EPI, BN / 32, 1, 2>(g, &tmC, s_bias, s_gate, gate_in_smem, taddr, smem_u32(smem) + STAGES * Cfg::STAGE_BYTES + quad * 8192,
+                                                 sbuf, m_blk * 128 + quad * 32, n0, lane, 0);
             } else if (!done) {
                 constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -727,27 +742,38 @@ struct Gemm2Cfg {
     static constexpr int A_BYTES = 128 * BK * 2;
     static constexpr int BH_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2048;
+    static constexpr int STAGING_BYTES = 8 * 4096;               // eight epilogue warps, one 32-row x 128-B buffer each
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 2048;
+    static constexpr int THREADS = 384;                          // 4 control warps + 8 epilogue warps
     static_assert(BH_BYTES % 1024 == 0, "B half tile must stay 1024-B aligned");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+__device__ __forceinline__ void epi2_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmE, const GemmArgs g) {
     using Cfg = Gemm2Cfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BK = 64;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    constexpr bool kTmaEpi = gemm_tma_epilogue(EPI, BN);
+    constexpr bool kHeadsTma = EPI == EPI_HEADS && BN % HG == 0;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    constexpr int OFF_STG = STAGES * Cfg::STAGE_BYTES;
+    constexpr int OFF_BAR = OFF_STG + Cfg::STAGING_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BAR + 256);
     float* s_gate = s_bias + 256;
 
     const int warp = threadIdx.x >> 5;
@@ -758,6 +784,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if constexpr (kTmaEpi || kHeadsTma) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -766,7 +793,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 256); // epilogue threads of both CTAs
+            mbar_init(&tempty_bar[s], 16);  // one elected lane of each of the 8 epilogue warps of both CTAs
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -779,9 +806,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();                     // barriers of both CTAs initialised before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // Launched WITHOUT programmatic dependent launch and without an early trigger: chains of PDL-overlapped cluster
-    // kernels hung intermittently on B200 (profiles/README.md, open issue), so this kernel is fully stream-serialised.
+    long long* const dbg = g.dbg != nullptr ? g.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long t_entry = dbg != nullptr ? clock64() : 0;
+    if (g.pdl_trigger != 0) pdl_launch_dependents();
     pdl_wait();   // no-op for a normally launched grid
+    if (dbg != nullptr && threadIdx.x == 0) { dbg[0] = clock64(); dbg[13] = t_entry; }
 
     const int tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + 255) / 256;
@@ -793,10 +822,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t full0 = smem_u32(&full_bar[0]) & kPeerBitMask;      // the leader's barriers, from either CTA
         int stage = 0;
         uint32_t phase = 0;
+        long long w_empty = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             for (int kb = 0; kb < num_kb; ++kb) {
+                const long long tw = dbg != nullptr ? clock64() : 0;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (dbg != nullptr) w_empty += clock64() - tw;
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -807,6 +839,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (dbg != nullptr && lane == 0) { dbg[5] = w_empty; dbg[6] = clock64(); }
     } else if (warp == 1) {
         if (leader) {
             constexpr uint32_t idesc = umma_idesc_f16(256, BN);
@@ -816,12 +849,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long w_full = 0, w_tempty = 0, t_first = 0;
+            int ntile = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                long long tw = dbg != nullptr ? clock64() : 0;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                if (dbg != nullptr) w_tempty += clock64() - tw;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_u + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    tw = dbg != nullptr ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase);
+                    if (dbg != nullptr) { const long long tn = clock64(); w_full += tn - tw; if (ntile == 0 && kb == 0) t_first = tn; }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
                     const uint64_t adesc = umma_desc_kmajor<128>(a_addr);
@@ -837,21 +876,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (elect_one()) umma_commit_2sm(&tfull_bar[acc]);
                 __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                ++ntile;
             }
+            if (dbg != nullptr && lane == 0) { dbg[1] = t_first; dbg[2] = clock64(); dbg[3] = w_full; dbg[4] = w_tempty; }
         }
     } else if (warp >= 4) {
-        const int quad = warp & 3;
+        const int quad = warp & 3;              // TMEM lane quadrant = warp id % 4
+        const int part = (warp - 4) >> 2;       // which half of the column units this warp takes
         const int et = threadIdx.x - 128;
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool gate_in_smem = (EPI == EPI_GATED) && (g.rows_per_batch % 128 == 0);
         const uint32_t tempty0 = smem_u32(&tempty_bar[0]) & kPeerBitMask;
+        const uint32_t stg = smem_u32(smem) + OFF_STG + (warp - 4) * 4096;
+        long long w_tfull = 0, t_proc = 0;
+        uint32_t sbuf = 0;
+        int ntile = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             const int n0 = n_blk * BN;
             const int row0 = m_blk * 256 + static_cast<int>(rank) * 128;
-            epi_bar_sync();
-            for (int c = et; c < BN; c += 128) {
+            epi2_bar_sync();
+            for (int c = et; c < BN; c += 256) {
                 const int col = n0 + c;
                 s_bias[c] = (g.bias != nullptr && col < g.N) ? __half2float(g.bias[col]) : 0.f;
                 if constexpr (EPI == EPI_GATED) {
@@ -861,37 +907,64 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             }
-            epi_bar_sync();
-            const int row = row0 + quad * 32 + lane;
-            const bool row_ok = row < g.M;
-            HeadCursor hc{0, 0, 0, 0, 0};
-            size_t head_row_off = 0;
-            if constexpr (EPI == EPI_HEADS) {
-                hc.which = n0 / g.split_cols;
-                const int c = n0 - hc.which * g.split_cols;
-                hc.head = c / g.Dh;
-                hc.d = c - hc.head * g.Dh;
-                hc.b = row / g.Nseq;
-                hc.n = row - hc.b * g.Nseq;
-                head_row_off = (static_cast<size_t>(hc.b) * g.H * g.Nseq + hc.n) * g.DhP;
-            }
+            epi2_bar_sync();
+            const long long tw = dbg != nullptr ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
+            const long long tp = dbg != nullptr ? clock64() : 0;
+            w_tfull += tp - tw;
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            bool done = false;
+            if constexpr (kHeadsTma) {
+                if (g.heads_tma != 0) {
+                    epilogue_heads_tma<BN / HG, 2, 1>(g, &tmC, &tmD, &tmE, s_bias, taddr, stg, sbuf, row0 + quad * 32, n0, lane, part);
+                    done = true;
+                }
+            }
+            if constexpr (kTmaEpi) {
+                epilogue_tma<EPI, BN / 32, 2, 1>(g, &tmC, s_bias, s_gate, gate_in_smem, taddr, stg, sbuf, row0 + quad * 32, n0, lane, part);
+            } else if (!done) {
+                // per-thread path (ragged head split / tile widths the bulk stores do not cover): this warp takes every second chunk
+                const int row = row0 + quad * 32 + lane;
+                const bool row_ok = row < g.M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c0, r);
-                tmem_ld_wait();
-                epi_chunk<EPI, 32>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
+                for (int c0 = part * 32; c0 < BN; c0 += 64) {
+                    HeadCursor hc{0, 0, 0, 0, 0};
+                    size_t head_row_off = 0;
+                    if constexpr (EPI == EPI_HEADS) {
+                        hc.which = (n0 + c0) / g.split_cols;
+                        const int c = (n0 + c0) - hc.which * g.split_cols;
+                        hc.head = c / g.Dh;
+                        hc.d = c - hc.head * g.Dh;
+                        hc.b = row / g.Nseq;
+                        hc.n = row - hc.b * g.Nseq;
+                        head_row_off = (static_cast<size_t>(hc.b) * g.H * g.Nseq + hc.n) * g.DhP;
+                    }
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    epi_chunk<EPI, 32>(g, s_bias, s_gate, gate_in_smem, row, row_ok, n0 + c0, c0, r, hc, head_row_off);
+                }
             }
             tc_fence_before();
-            mbar_arrive_cluster(tempty0 + acc * 8);     // leader's tempty, from both CTAs
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + acc * 8);     // leader's tempty, from both CTAs
+            if (dbg != nullptr) t_proc += clock64() - tp;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ++ntile;
         }
+        if constexpr (kTmaEpi || kHeadsTma) {
+            if (lane == 0) bulk_wait<0>();
+        }
+        if (dbg != nullptr && et == 0) { dbg[7] = w_tfull; dbg[8] = t_proc; dbg[9] = clock64(); dbg[10] = ntile; }
     }
     tc_fence_before();
     cluster_sync_all();                     // neither CTA may exit (or free TMEM) while its peer can still signal / read it
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[14] = clock64(); dbg[15] = smid;
+    }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");

@@ -79,9 +79,17 @@ def main():
         ("qkv store", 4096, 3456, 1152, "store", 192),
         ("proj gated", 4096, 1152, 1152, "gated", 128),
         ("proj store", 4096, 1152, 1152, "store", 128),
-        ("to_q heads (M=2048)", 2048, 1152, 1152, "heads", 128),
+        ("to_q heads (M=2048)", 2048, 1152, 1152, "heads", 144),
         ("cproj gated (M=2048)", 2048, 1152, 1152, "gated", 128),
+        ("2cta fc1 gelu", 4096, 4608, 1152, "gelu", -256),
+        ("2cta fc2 gated", 4096, 1152, 4608, "gated", -128),
+        ("2cta qkv heads", 4096, 3456, 1152, "heads", -192),
+        ("2cta proj gated", 4096, 1152, 1152, "gated", -128),
+        ("2cta to_q heads (M=2048)", 2048, 1152, 1152, "heads", -144),
+        ("2cta cproj gated (M=2048)", 2048, 1152, 1152, "gated", -128),
     ]:
+        if len(sys.argv) > 1 and sys.argv[1] not in name:
+            continue
         run(name, M, N, K, kind, tile)
 
 

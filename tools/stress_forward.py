@@ -9,9 +9,10 @@ m = tpxl_b200.DiT(**synth.FULL_DIT); m.load_state_dict(sd); m = m.to(dev); del s
 x = torch.randn(1, 2048, 68, device=dev); y = torch.randn(1, 1370, 768, device=dev); t = torch.tensor([960], device=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 sync_every = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+t0 = time.perf_counter()
 for i in range(n):
     o = m.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True)
     if (i + 1) % sync_every == 0:
         torch.cuda.synchronize()
-        print("iter", i, float(o.float().abs().mean()), flush=True)
+        print("iter", i, float(o.float().abs().mean()), f"{(time.perf_counter() - t0) / (i + 1) * 1e3:.3f} ms/forward", flush=True)
 print("done", flush=True)
