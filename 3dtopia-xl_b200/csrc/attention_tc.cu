@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
                     const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
                     int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_cycles, int flags) {
-    extern __shared__ uint8_t ta_smem_raw[];
+    extern __shared__ __align__(1024) uint8_t ta_smem_raw[];
     // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
     // access to generic LD/ST instead of LDS/STS)
     uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);
@@ -468,6 +468,375 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
     }
 }
 
+
+// =====================================================================================================================
+// Software-pipelined variant of attention_tc_kernel (same roles, layouts, barriers).  Measured (tools/attn_timeline.py): a
+// softmax warp spends ~1000 cycles of every ~3300-cycle tile outside its exponentials — barrier polls, the tcgen05.ld of the
+// score row, the wait for the single P buffer, fence + arrive — and the two warpgroups drift into phase, so those cycles
+// are not covered by the other warp's MUFU work.  Here the warp covers them itself:
+//   * the first 32 scores of tile j+1 are pulled into spare registers while tile j's last chunk is exponentiated, and the
+//     other 96 are loaded under the first chunk's exponentials (no exposed tcgen05.ld / s_full poll);
+//   * the first chunk is exponentiated into registers BEFORE the wait for P V(j-1) (the P buffer), which hides that wait.
+// =====================================================================================================================
+// POLY: every POLY-th exponential of a full tile is evaluated by ex2_poly instead of MUFU.EX2 (0 = none).
+template <int POLY>
+__global__ void __launch_bounds__(TA_THREADS, 1)
+attention_tc_p_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
+                    const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
+                    int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_cycles, int flags) {
+    extern __shared__ __align__(1024) uint8_t ta_smem_raw[];
+    // 1024-B alignment by pointer arithmetic on the __shared__ array (an integer round trip would demote every later
+    // access to generic LD/ST instead of LDS/STS)
+    uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TA_OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // TA_KV_STAGES
+    uint64_t* kv_empty = bars + 4;      // TA_KV_STAGES
+    uint64_t* s_full = bars + 7;        // 2 (per query tile)
+    uint64_t* s_free = bars + 9;        // 2
+    uint64_t* p_full = bars + 11;       // 2
+    uint64_t* o_full = bars + 13;       // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (2 * TA_BQ);
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int bh = b * H + h;
+    const int nkt = (Nk + TA_BKV - 1) / TA_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQa); tma_prefetch_desc(&tmQb); tma_prefetch_desc(&tmKa); tma_prefetch_desc(&tmKb); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < TA_KV_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 2);      // one commit from each of the two MMA issuer warps
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+    // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464)
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, 2 * TA_Q_BYTES);
+            for (int X = 0; X < 2; ++X) {
+                uint8_t* qs = smem + TA_OFF_Q + X * TA_Q_BYTES;
+                const int row = bh * Nq + q0 + X * TA_BQ;
+                tma_load_2d(qs, &tmQa, q_full, 0, row);
+                tma_load_2d(qs + 128 * 128, &tmQb, q_full, 64, row);
+            }
+        }
+        __syncwarp();
+        for (int j = 0; j < nkt; ++j) {
+            const int s = j % TA_KV_STAGES;
+            mbar_wait(&kv_empty[s], ((j / TA_KV_STAGES) & 1) ^ 1);
+            if (elect_one()) {
+                uint8_t* ks = smem + TA_OFF_KV + s * TA_KV_STAGE;
+                uint8_t* vs = ks + TA_K_BYTES;
+                mbar_arrive_expect_tx(&kv_full[s], TA_KV_STAGE);
+                const int krow = bh * Nk + j * TA_BKV;
+                tma_load_2d(ks, &tmKa, &kv_full[s], 0, krow);
+                tma_load_2d(ks + 128 * 128, &tmKb, &kv_full[s], 64, krow);
+                tma_load_2d(vs, &tmV, &kv_full[s], j * TA_BKV, bh * TA_DHP);
+                tma_load_2d(vs + TA_VBOX_BYTES, &tmV, &kv_full[s], j * TA_BKV + 64, bh * TA_DHP);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1 || warp == 3) {
+        // Two warp-converged issuer warps (uniform control flow, one elected lane issues; descriptors stay in uniform
+        // registers): warp 1 drives query tile A, warp 3 tile B, so the two softmax warpgroups run as independent pipelines
+        // and can de-phase instead of being re-synchronised by one in-order issuer.
+        const int X = warp == 1 ? 0 : 1;
+        constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
+        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+        auto issue_qk = [&](int X, int s) {
+            const uint32_t qa = sbase + TA_OFF_Q + X * TA_Q_BYTES, ka = sbase + TA_OFF_KV + s * TA_KV_STAGE;
+            const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
+            const uint64_t dq2 = umma_desc_kmajor<32>(qa + 128 * 128), dk2 = umma_desc_kmajor<32>(ka + 128 * 128);
+            const uint32_t ts = tbase + X * 128;
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(ts, dq + 2 * i, dk + 2 * i, idesc_qk, i > 0 ? 1u : 0u);
+                umma_f16(ts, dq2, dk2, idesc_qk, 1u);
+                umma_commit(&s_full[X]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int X, int s, uint32_t acc_first) {
+            const uint32_t pa = sbase + TA_OFF_P + X * TA_P_BYTES, va = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES;
+            const uint32_t to = tbase + 256 + X * 128;
+            const uint64_t dp0 = umma_desc_kmajor<128>(pa), dv0 = umma_desc_kmajor<128>(va);
+            const uint64_t dp1 = umma_desc_kmajor<128>(pa + 128 * 128), dv1 = umma_desc_kmajor<128>(va + TA_VBOX_BYTES);
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(to, dp0 + 2 * i, dv0 + 2 * i, idesc_pv, i != 0 ? 1u : acc_first);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_f16(to, dp1 + 2 * i, dv1 + 2 * i, idesc_pv, 1u);
+                umma_commit(&o_full[X]);
+            }
+            __syncwarp();
+        };
+        // Row sums on the tensor core: row Dh of every V^T tile (a padding row, Dh < 80) is overwritten with ones after the TMA
+        // lands, so column Dh of O accumulates sum_k P[r,k] — rescaled together with O — and the softmax threads carry no sum.
+        // Both issuer warps write the same 2 x 128 bytes (row 72 is swizzle row 0: identity chunk order).
+        auto write_ones = [&](int s) {
+            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + TA_SUMROW * 128 + lane * 4;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + TA_VBOX_BYTES), "r"(0x3C003C00u) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        write_ones(0);
+        tc_fence_after();
+        issue_qk(X, 0);
+        for (int j = 0; j < nkt; ++j) {
+            const int s = j % TA_KV_STAGES;
+            if (j + 1 < nkt) {           // next scores first: the warpgroup gets S(j+1) while it exponentiates tile j
+                const int sn = (j + 1) % TA_KV_STAGES;
+                mbar_wait(&kv_full[sn], ((j + 1) / TA_KV_STAGES) & 1);
+                write_ones(sn);
+                mbar_wait(&s_free[X], j & 1);
+                tc_fence_after();
+                issue_qk(X, sn);
+            }
+            mbar_wait(&p_full[X], j & 1);
+            tc_fence_after();
+            issue_pv(X, s, j > 0 ? 1u : 0u);      // O_X accumulates in TMEM across key tiles
+            if (elect_one()) umma_commit(&kv_empty[s]);
+            __syncwarp();
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int X = (warp - 4) >> 2;               // query tile of this warpgroup
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;              // row in the tile == TMEM lane
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t tS = tmem_base + X * 128 + lane_off;
+        const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
+        const uint32_t pS = smem_u32(smem) + TA_OFF_P + X * TA_P_BYTES + r * 128;   // shared-window address of this row of P
+        const int sw = r & 7;
+        float m_ref = 0.f;
+        const bool stale_max = (flags & 1) != 0;
+        auto rescale_o = [&](bool need, float mx) {
+            const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
+            if (need) m_ref = mx;
+            uint32_t t[32];
+            tmem_ld_32x32(tO, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+            tmem_st_32x32(tO, t);
+            tmem_ld_32x32(tO + 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+            tmem_st_32x32(tO + 32, t);
+            tmem_ld_32x16(tO + 64, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+            tmem_st_32x16(tO + 64, t);
+            tmem_st_wait();
+        };
+        // exponentials of one 32-score chunk against msc -> 16 packed fp16 pairs; optional running max (two chains)
+        auto exp_chunk = [&](const uint32_t* sc, int c, float msc, uint32_t (&pk)[16], bool track, float& m0, float& m1) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float s0 = __uint_as_float(sc[i]), s1 = __uint_as_float(sc[i + 1]);
+                const float s2 = __uint_as_float(sc[i + 2]), s3 = __uint_as_float(sc[i + 3]);
+                if (track) { m0 = fmaxf(m0, fmaxf(s0, s2)); m1 = fmaxf(m1, fmaxf(s1, s3)); }
+                const float p0 = (POLY > 0 && (c * 32 + i) % POLY == 0) ? ex2_poly(fmaf(s0, scale_log2, -msc)) : ex2(fmaf(s0, scale_log2, -msc));
+                const float p1 = (POLY > 0 && (c * 32 + i + 1) % POLY == 0) ? ex2_poly(fmaf(s1, scale_log2, -msc)) : ex2(fmaf(s1, scale_log2, -msc));
+                const float p2 = (POLY > 0 && (c * 32 + i + 2) % POLY == 0) ? ex2_poly(fmaf(s2, scale_log2, -msc)) : ex2(fmaf(s2, scale_log2, -msc));
+                const float p3 = (POLY > 0 && (c * 32 + i + 3) % POLY == 0) ? ex2_poly(fmaf(s3, scale_log2, -msc)) : ex2(fmaf(s3, scale_log2, -msc));
+                __half2 ha = __floats2half2_rn(p0, p1), hb = __floats2half2_rn(p2, p3);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&ha);
+                pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+        };
+        auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {
+            const uint32_t dst = pS + (c >> 1) * (128 * 128);
+            const int cc0 = (c & 1) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((cc0 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                             "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                             : "memory");
+        };
+
+        // prologue: the first 32 scores of tile 0
+        uint32_t nxt[32];
+        mbar_wait(&s_full[X], 0);
+        tc_fence_after();
+        if (X == 1 && stagger_cycles != 0) {
+            const long long t_end = clock64() + stagger_cycles;
+            while (clock64() < t_end) {}
+        }
+        tmem_ld_32x32(tS, nxt);
+        tmem_ld_wait();
+        for (int j = 0; j < nkt; ++j) {
+            const int nvalid = Nk - j * TA_BKV;      // keys of this tile that exist (>= 1)
+            uint32_t sv[128];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[i] = nxt[i];
+            if (r == 0) TA_DBG(X, 2);
+            // the other 96 scores load under the first chunk's exponentials
+            tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+            tmem_ld_32x32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(sv[64]));
+            tmem_ld_32x32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(sv[96]));
+            const bool fast = j > 0 && nvalid >= TA_BKV && stale_max;
+            if (fast) {
+                const float msc = m_ref * scale_log2;
+                float m0 = -INFINITY, m1 = -INFINITY;
+                uint32_t pk[16];
+                exp_chunk(&sv[0], 0, msc, pk, true, m0, m1);                 // into registers: the P buffer may still be read by P V(j-1)
+                mbar_wait(&o_full[X], (j - 1) & 1);                          // P V(j-1) retired: P_X may be rewritten, O_X is quiescent
+                tc_fence_after();
+                if (r == 0) TA_DBG(X, 5);
+                store_chunk(0, pk);
+                tmem_ld_wait();                                              // chunks 1..3 have been in flight for a whole chunk of exponentials
+                tc_fence_before();
+                mbar_arrive(&s_free[X]);                                     // the score row is in registers: S_X may be overwritten by Q K^T(j+1)
+                if (r == 0) TA_DBG(X, 3);
+                exp_chunk(&sv[32], 1, msc, pk, true, m0, m1);
+                store_chunk(1, pk);
+                exp_chunk(&sv[64], 2, msc, pk, true, m0, m1);
+                store_chunk(2, pk);
+                if (j + 1 < nkt) {                                           // Q K^T(j+1) was issued at s_free: normally complete by now
+                    mbar_wait(&s_full[X], (j + 1) & 1);
+                    tc_fence_after();
+                    tmem_ld_32x32(tS, nxt);                                  // first chunk of the next tile, lands under chunk 3's exponentials
+                }
+                exp_chunk(&sv[96], 3, msc, pk, true, m0, m1);
+                store_chunk(3, pk);
+                const float mx = fmaxf(m0, m1);
+                const bool need = (mx - m_ref) * scale_log2 > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {             // rare: redo this tile against the new maximum
+                    tmem_ld_wait();
+                    rescale_o(need, mx);
+                    const float msc2 = m_ref * scale_log2;
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        exp_chunk(&sv[c * 32], c, msc2, pk, false, d0, d1);
+                        store_chunk(c, pk);
+                    }
+                }
+            } else {
+                // first tile, ragged last tile (or stale_max off): maximum first, then the exponentials
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&s_free[X]);
+                if (r == 0) TA_DBG(X, 3);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                if (j > 0) {
+                    mbar_wait(&o_full[X], (j - 1) & 1);          // P V(j-1) retired: O_X quiescent, P_X free
+                    tc_fence_after();
+                }
+                if (j == 0) {
+                    m_ref = mx;
+                } else {
+                    const bool need = (mx - m_ref) * scale_log2 > 8.0f;
+                    if (__any_sync(0xffffffffu, need)) rescale_o(need, mx);
+                }
+                const float msc = m_ref * scale_log2;
+                if (r == 0) TA_DBG(X, 5);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
+                        float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
+                        if (c * 32 + i >= nvalid) p0 = 0.f;
+                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+                        __half2 hh = __floats2half2_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                    store_chunk(c, pk);
+                }
+                if (j + 1 < nkt) {
+                    mbar_wait(&s_full[X], (j + 1) & 1);
+                    tc_fence_after();
+                    tmem_ld_32x32(tS, nxt);
+                }
+            }
+            if (r == 0) TA_DBG(X, 6);
+            fence_proxy_async();            // make the P stores visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(&p_full[X]);
+            tmem_ld_wait();                 // nxt (first chunk of tile j+1) is valid
+            if (r == 0) TA_DBG(X, 7);
+            if (r == 0) TA_DBG(X, 1);
+        }
+        mbar_wait(&o_full[X], (nkt - 1) & 1);
+        tc_fence_after();
+        const int row = q0 + X * TA_BQ + r;
+        __half* orow = out + (static_cast<size_t>(b) * Nq + (row < Nq ? row : 0)) * (H * Dh) + h * Dh;
+        uint32_t t2[32];
+        tmem_ld_32x16(tO + 64, t2);                  // columns 64..79: the last 8 value columns and, at column Dh, the row sum
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(t2[TA_SUMROW - 64]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t t[32];
+            if (c < 2) {
+                tmem_ld_32x32(tO + c * 32, t);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = t2[i];
+            }
+#pragma unroll
+            for (int d8 = 0; d8 < (c < 2 ? 32 : 16); d8 += 8) {
+                const int d = c * 32 + d8;
+                if (row < Nq && d < Dh) {
+                    Pack8 v;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn(__uint_as_float(t[d8 + i]) * inv);
+                    *reinterpret_cast<uint4*>(orow + d) = v.u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+
 }  // namespace
 
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
@@ -484,18 +853,21 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 64, &mKa)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 128, 16, &mKb)) != TPX_OK) return rc;
     if ((rc = make_tensor_map_2d(vT, static_cast<long long>(B) * H * TA_DHP, NkPad, NkPad, TA_DHP, 64, &mV)) != TPX_OK) return rc;
-    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 0;   // 4: every 4th exponential as a cubic on the FMA pipe — faster in isolation (ubench), slower in the kernel; off
-    auto kern = poly == 0 ? attention_tc_kernel<0> : attention_tc_kernel<4>;
+    static const int poly = getenv("TPX_ATT_POLY") ? atoi(getenv("TPX_ATT_POLY")) : 0;   // 4: every 4th exponential as a cubic on the FMA pipe
+    static const int variant = getenv("TPX_ATT_VARIANT") ? atoi(getenv("TPX_ATT_VARIANT")) : 1;   // 1: software-pipelined softmax warps (default); 0: the plain loop
     static bool attr_set = false;
     if (!attr_set) {
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        TPX_CUDA(cudaFuncSetAttribute(attention_tc_p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
     static const unsigned stagger = getenv("TPX_ATT_STAGGER") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER"))) : 1600u;   // cycles; see the de-phasing note in the kernel
     static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
+    auto kern = variant == 0 ? (poly == 0 ? attention_tc_kernel<0> : attention_tc_kernel<4>) : (poly == 0 ? attention_tc_p_kernel<0> : attention_tc_p_kernel<4>);
     TPX_CUDA(launch_pdl(kern, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
                         stale_max ? 1 : 0));
     TPX_LAUNCH_CHECK();
