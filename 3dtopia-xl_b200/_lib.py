@@ -84,11 +84,14 @@ def load_library(path: str | None = None) -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        p = path or LIB_PATH
+        override = os.environ.get("TPX_LIB_PATH")       # tuning aid: A/B an older build of the library (symbols it lacks are skipped)
+        p = path or override or LIB_PATH
         if not os.path.exists(p):
             raise TpxError(f"{p} not found: build it with `python 3dtopia-xl_b200/build.py` (there is no fallback path)")
         lib = C.CDLL(p)
         for name, (res, args) in SIGNATURES.items():
+            if override and not path and not hasattr(lib, name):
+                continue
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         _lib = lib

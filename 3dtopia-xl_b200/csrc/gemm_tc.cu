@@ -157,6 +157,36 @@ static int map_conv(const void* ptr, long long P, int S, int C, int bk, CUtensor
     return TPX_OK;
 }
 
+int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes,
+                       CUtensorMap* out);
+// General fp16 tensor map (rank <= 5, dims / strides innermost first, strides in bytes for dims 1..rank-1); not cached.
+int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes,
+                       CUtensorMap* out) {
+    EncodeTiledFn enc = encode_fn();
+    TPX_CHECK(enc != nullptr, TPX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+    TPX_CHECK(rank >= 1 && rank <= 5 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, TPX_ERR_ARG, "tensor map: rank %d / unaligned base", rank);
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = static_cast<cuuint64_t>(dims[i]);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        estr[i] = 1;
+        if (i > 0) {
+            TPX_CHECK(strides_bytes[i - 1] % 16 == 0, TPX_ERR_ARG, "tensor map: stride %lld of dim %d is not a multiple of 16 bytes", strides_bytes[i - 1], i);
+            gstr[i - 1] = static_cast<cuuint64_t>(strides_bytes[i - 1]);
+        }
+    }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TPX_CHECK(r == CUDA_SUCCESS, TPX_ERR_CUDA, "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, static_cast<int>(r));
+    return TPX_OK;
+}
+
 int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out) {
     return map_2d(ptr, rows, cols, ld, box_rows, box_cols, out);
 }
@@ -190,6 +220,13 @@ static int make_output_maps(const GemmProblem& p, GemmArgs& a, const CUtensorMap
         if (p.epi == EPI_GATED) {
             TPX_CHECK(a.xres != nullptr && a.gate != nullptr, TPX_ERR_ARG, "gemm: gated epilogue without residual / gate");
             rc = map_2d(a.xres, p.M, p.N, a.ldx, 32, 32, &tc, 4);
+        } else if (a.convt_store != 0) {
+            // out0 already points at the (a,b,c) corner of the [P, 8, 8, 8, N] volume: the stride-2 sub-lattice as a 5-D tensor
+            TPX_CHECK(a.out0 != nullptr && p.M % 64 == 0 && p.epi == EPI_STORE, TPX_ERR_ARG, "gemm: transposed-conv store needs EPI_STORE and M = P * 64");
+            const long long C = p.N, dims[5] = {C, 4, 4, 4, p.M / 64};
+            const long long strides[4] = {2 * C * 2, 16 * C * 2, 128 * C * 2, 512 * C * 2};
+            const int box[5] = {64, 4, 4, 2, 1};
+            rc = make_tensor_map_nd(a.out0, 5, dims, strides, box, 128, &tc);
         } else {
             TPX_CHECK(a.out0 != nullptr && a.ldo >= p.N, TPX_ERR_ARG, "gemm: output pointer / row stride (%d < N %d)", a.ldo, p.N);
             rc = map_2d(a.out0, p.M, p.N, a.ldo, 32, 64, &tc, 2);

@@ -45,6 +45,8 @@ struct GemmArgs {
     float alpha;
     float* out32;
     int n_valid, S3;
+    int convt_store;  // EPI_STORE: 1 = rows are (primitive, 4^3 voxel) and the output map is the 5-D stride-2 lattice of one (a,b,c) offset of
+                      // a ConvTranspose3d(k2,s2): a warp's 32 rows are one [2 z][4 y][4 x] box (vae3d_dib.py:220-226)
     int pdl_trigger;  // 2-CTA kernel: 1 = griddepcontrol.launch_dependents after the prologue (launched with the PDL attribute)
     int heads_tma;    // EPI_HEADS: 1 = outputs leave as 24-column bulk tensor stores (launcher checked the geometry, padding is pre-zeroed)
     long long* dbg;   // timeline probe (tpx_debug_gemm_timeline): 16 int64 per CTA, nullptr in the product path
@@ -375,7 +377,8 @@ __device__ __forceinline__ void epilogue_tma(const GemmArgs& g, const CUtensorMa
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(tmC, stg + boff, n0 + (k - 1) * 32, row0);
+                    if (g.convt_store != 0) tma_store_5d(tmC, stg + boff, n0 + (k - 1) * 32, 0, 0, (row0 & 63) >> 4, row0 >> 6);
+                    else tma_store_2d(tmC, stg + boff, n0 + (k - 1) * 32, row0);
                     bulk_commit();
                 }
                 ++sbuf;
@@ -514,7 +517,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    long long* const dbg = g.dbg != nullptr ? g.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    // timeline probe: compiled only into the wide linear kernels it was written for — in the narrow-tile convolution kernels the MMA
+    // issuer has ~64 cycles per k-block and the (never taken) probe branches cost 14 % there
+    constexpr bool kProbe = AMODE == AMODE_LINEAR && BN >= 128;
+    long long* const dbg = (kProbe && g.dbg != nullptr) ? g.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
     const long long t_entry = dbg != nullptr ? clock64() : 0;
     pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
     pdl_wait();                // ... and ours ends here: the operands written by the previous kernel are now visible

@@ -143,6 +143,8 @@ VaeWs carve_vws(const tpx_vae* h, int P, uint8_t* base) {
 
 int conv3(const __half* x, const __half* W, const __half* bias, const __half* resid, float alpha, __half* out, float* out32, int n_valid, int P, int S,
           int C, int Cout, int epi, cudaStream_t st) {
+    // 8^3 layers with narrow outputs: the input block is staged once per output tile (conv_halo.cu) instead of once per tap
+    if (conv3_halo_supported(S, C, Cout, epi)) return launch_conv3_halo(x, W, bias, resid, alpha, out, out32, n_valid, P, C, Cout, epi, st);
     GemmProblem p{};
     p.A = x; p.a_mode = AMODE_CONV3; p.conv_S = S; p.conv_C = C; p.W = W;
     p.M = P * S * S * S; p.N = Cout; p.K = 27 * C; p.BN = Cout; p.epi = epi;
@@ -284,13 +286,18 @@ int tpx_vae_decode(tpx_vae* h, const void* z, int z_dtype, void* out, int out_dt
     TPX_RC(res4(h->res[1]));
     TPX_RC(res4(h->res[2]));
     TPX_RC(res4(h->res[3]));
-    {   // ConvTranspose3d(k2,s2): 8 independent 1x1 GEMMs fused into one N = 8*C0 GEMM with a scatter epilogue
-        GemmProblem p{};
-        p.A = X; p.a_mode = AMODE_LINEAR; p.lda = C0; p.W = h->Wup; p.M = P * 64; p.N = 8 * C0; p.K = C0; p.BN = 256; p.epi = EPI_CONVT2;
-        GemmArgs a{};
-        a.bias = h->bup; a.post_scale = 1.0f; a.out0 = w.U; a.split_cols = C0;
-        p.args = a;
-        TPX_RC(launch_gemm(p, st));
+    {   // ConvTranspose3d(k2,s2): 8 independent 1x1 GEMMs, one per output offset (a,b,c); each writes its stride-2 sub-lattice of the
+        // 8^3 volume with bulk tensor stores (full 128-B lines; the single N = 8*C0 GEMM with a per-thread scatter epilogue was store-bound)
+        for (int abc = 0; abc < 8; ++abc) {
+            GemmProblem p{};
+            p.A = X; p.a_mode = AMODE_LINEAR; p.lda = C0; p.W = h->Wup + static_cast<size_t>(abc) * C0 * C0; p.M = P * 64; p.N = C0; p.K = C0; p.BN = 256;
+            p.epi = EPI_STORE;
+            GemmArgs a{};
+            a.bias = h->bup + static_cast<size_t>(abc) * C0; a.post_scale = 1.0f; a.ldo = C0; a.convt_store = 1;
+            a.out0 = w.U + (static_cast<size_t>((abc >> 2) * 8 + ((abc >> 1) & 1)) * 8 + (abc & 1)) * C0;
+            p.args = a;
+            TPX_RC(launch_gemm(p, st));
+        }
     }
     {   // ResnetBlock C0 -> C1 at 8^3 with 1x1 shortcut
         const VaeRes& r = h->res[4];

@@ -55,7 +55,18 @@ int launch_vae_conv_in(const void* z, int z_dtype, const __half* w_pq, const __h
 // partial sums meet in shared memory, then a second streaming pass normalises (the re-read hits L2).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GN_MAXC = 256;
-__global__ void __launch_bounds__(256) groupnorm_silu_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (relative error ~2e-7, far below the fp16 rounding of the result)
+__device__ __forceinline__ float silu_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+// RES > 0: the primitive's S3 * C / 8 octets are exactly RES per thread and stay in registers between the statistics and the
+// normalisation (one read, RES loads in flight per thread: the 32 KB volumes of the 4^3 stage and of the 32-channel 8^3 stage);
+// RES == 0: streaming two-pass version for larger volumes.
+template <int RES>
+__global__ void __launch_bounds__(256, RES > 0 ? 3 : 1) groupnorm_silu_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                                              const __half* __restrict__ beta, int S3, int C, int groups, float eps, int apply_silu,
                                                              __half* __restrict__ out) {
     __shared__ float s_sum[GN_MAXC], s_sq[GN_MAXC], s_scale[GN_MAXC], s_shift[GN_MAXC];
@@ -69,14 +80,30 @@ __global__ void __launch_bounds__(256) groupnorm_silu_kernel(const __half* __res
     float ls[8], lq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ls[i] = 0.f; lq[i] = 0.f; }
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        Pack8 v;
-        v.u = xp[i];
+    Pack8 keep[RES > 0 ? RES : 1];
+    if constexpr (RES > 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float f = __half2float(v.h[k]);
-            ls[k] += f;
-            lq[k] = fmaf(f, f, lq[k]);
+        for (int j = 0; j < RES; ++j) keep[j].u = xp[threadIdx.x + j * 256];
+#pragma unroll
+        for (int j = 0; j < RES; ++j) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float f = __half2float(keep[j].h[k]);
+                ls[k] += f;
+                lq[k] = fmaf(f, f, lq[k]);
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            Pack8 v;
+            v.u = xp[i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float f = __half2float(v.h[k]);
+                ls[k] += f;
+                lq[k] = fmaf(f, f, lq[k]);
+            }
         }
     }
     // deterministic cross-thread reduction (fixed order; run-to-run bit-identical): per-thread partials -> smem,
@@ -116,16 +143,31 @@ __global__ void __launch_bounds__(256) groupnorm_silu_kernel(const __half* __res
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = s_scale[my_oct * 8 + k]; sh[k] = s_shift[my_oct * 8 + k]; }
     uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * S3 * C);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        Pack8 v, o;
-        v.u = xp[i];
+    if constexpr (RES > 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float f = fmaf(__half2float(v.h[k]), sc[k], sh[k]);
-            if (apply_silu) f = silu(f);
-            o.h[k] = __float2half_rn(f);
+        for (int j = 0; j < RES; ++j) {
+            Pack8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float f = fmaf(__half2float(keep[j].h[k]), sc[k], sh[k]);
+                if (apply_silu) f = silu_fast(f);
+                o.h[k] = __float2half_rn(f);
+            }
+            op[threadIdx.x + j * 256] = o.u;
         }
-        op[i] = o.u;
+    } else {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            Pack8 v, o;
+            v.u = xp[i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float f = fmaf(__half2float(v.h[k]), sc[k], sh[k]);
+                if (apply_silu) f = silu_fast(f);
+                o.h[k] = __float2half_rn(f);
+            }
+            op[i] = o.u;
+        }
     }
 }
 
@@ -135,7 +177,8 @@ int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* be
               "groupnorm: channels %d / groups %d unsupported (C%%8==0, C<=%d, C/8 | 256)", C, groups, GN_MAXC);
     if (P <= 0) return TPX_OK;
     ProfScope prof(PROF_GROUPNORM, st);
-    groupnorm_silu_kernel<<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
+    if (S3 * (C / 8) == 8 * 256) groupnorm_silu_kernel<8><<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
+    else groupnorm_silu_kernel<0><<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
     TPX_LAUNCH_CHECK();
     return TPX_OK;
 }
