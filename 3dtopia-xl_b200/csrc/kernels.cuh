@@ -61,4 +61,9 @@ int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* be
 int launch_primsdf_query(const float* x, const float* srt, const float* feat, long long n, int K, int S, int dim_feat, int inference, float* out,
                          cudaStream_t st);
 
+size_t primsdf_grid_bytes(long long cap_entries);
+int launch_primsdf_grid_build(const float* srt, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_primsdf_query_grid(const float* x, const float* srt, const float* feat, const void* ws, size_t ws_bytes, long long n, int K, int S, int dim_feat,
+                              int inference, float* out, cudaStream_t st);
+
 }  // namespace tpx

@@ -332,6 +332,23 @@ int tpx_primsdf_query(const float* x, const float* srt, const float* feat, int64
     return launch_primsdf_query(x, srt, feat, n, K, S, dim_feat, inference, out, static_cast<cudaStream_t>(stream));
 }
 
+size_t tpx_primsdf_grid_bytes(int64_t cap_entries) { return cap_entries > 0 ? primsdf_grid_bytes(cap_entries) : 0; }
+
+int tpx_primsdf_grid_build(const float* srt, int K, void* grid_ws, size_t grid_bytes, void* stream) {
+    TPX_CHECK(srt != nullptr && grid_ws != nullptr, TPX_ERR_ARG, "primsdf_grid_build: null argument");
+    int rc = tpx_device_check();
+    if (rc != TPX_OK) return rc;
+    return launch_primsdf_grid_build(srt, K, grid_ws, grid_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int tpx_primsdf_query_grid(const float* x, const float* srt, const float* feat, const void* grid_ws, size_t grid_bytes, int64_t n, int K, int S, int dim_feat,
+                           int inference, float* out, void* stream) {
+    if (n == 0) return TPX_OK;
+    TPX_CHECK(n > 0 && x != nullptr && srt != nullptr && feat != nullptr && out != nullptr && grid_ws != nullptr, TPX_ERR_ARG,
+              "primsdf_query_grid: null argument or negative n");
+    return launch_primsdf_query_grid(x, srt, feat, grid_ws, grid_bytes, n, K, S, dim_feat, inference, out, static_cast<cudaStream_t>(stream));
+}
+
 int tpx_groupnorm_silu(const void* x, const void* gamma, const void* beta, int P, int S3, int C, int groups, float eps, int apply_silu, void* out,
                        void* stream) {
     TPX_CHECK(x != nullptr && gamma != nullptr && beta != nullptr && out != nullptr, TPX_ERR_ARG, "groupnorm_silu: null argument");

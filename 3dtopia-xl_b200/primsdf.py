@@ -29,6 +29,8 @@ class PrimSDF(nn.Module):
         self.geo_start_index, self.geo_end_index = 0, s3
         self.tex_start_index, self.tex_end_index = s3, 4 * s3
         self.mat_start_index, self.mat_end_index = 4 * s3, 6 * s3
+        self._grid = None          # (key, srt tensor the grid was built from, workspace): rebuilt whenever srt_param changes
+        self.grid_entries = 8 << 20   # capacity of the per-cell lists (int32 entries); over-full grids fall back to the exhaustive loop
 
     def forward(self, x: torch.Tensor):
         if x.dim() != 2 or x.shape[1] != 3:
@@ -42,8 +44,19 @@ class PrimSDF(nn.Module):
         n, K = xx.shape[0], srt.shape[0]
         out = torch.empty(n, self.dim_feat, dtype=torch.float32, device=xx.device)
         with torch.cuda.device(xx.device):
-            _lib.check(lib.tpx_primsdf_query(xx.data_ptr(), srt.data_ptr(), feat.data_ptr(), n, K, self.prim_shape, self.dim_feat,
-                                             0 if self.training else 1, out.data_ptr(), _lib.stream_ptr()), "tpx_primsdf_query")
+            if K < 1 or K > 4096:      # outside the grid builder's range: exhaustive kernel
+                _lib.check(lib.tpx_primsdf_query(xx.data_ptr(), srt.data_ptr(), feat.data_ptr(), n, K, self.prim_shape, self.dim_feat,
+                                                 0 if self.training else 1, out.data_ptr(), _lib.stream_ptr()), "tpx_primsdf_query")
+            else:
+                key = (self.srt_param.data_ptr(), self.srt_param._version, K, str(xx.device))
+                if self._grid is None or self._grid[0] != key:
+                    nbytes = int(lib.tpx_primsdf_grid_bytes(self.grid_entries))
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=xx.device)
+                    _lib.check(lib.tpx_primsdf_grid_build(srt.data_ptr(), K, ws.data_ptr(), nbytes, _lib.stream_ptr()), "tpx_primsdf_grid_build")
+                    self._grid = (key, self.srt_param.data, ws)     # holding the tensor keeps its address from being recycled under the key
+                ws = self._grid[2]
+                _lib.check(lib.tpx_primsdf_query_grid(xx.data_ptr(), srt.data_ptr(), feat.data_ptr(), ws.data_ptr(), ws.numel(), n, K, self.prim_shape,
+                                                      self.dim_feat, 0 if self.training else 1, out.data_ptr(), _lib.stream_ptr()), "tpx_primsdf_query_grid")
         return {"sdf": out[:, 0:1], "tex": out[:, 1:4], "mat": out[:, 4:6]}
 
     def sdf2alpha(self, sdf):

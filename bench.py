@@ -418,9 +418,9 @@ def run_ours(args):
     attn_tf = fx["attention"] / (ms_cls[1] / 1e3) / 1e12 if ms_cls[1] > 0 else 0.0
     step_ms_prof = sum(ms_cls)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
-    if not os.path.exists(tp):
-        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    tp = cands[-1] if cands else ""
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
@@ -436,13 +436,13 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "sample_steps_per_s": sample_steps_per_s,
         "clocks": clock_info,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA GEMM family, all DiT linears)", "achieved": gemm_tf, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel + gemm_tc2_kernel (tcgen05/TMA GEMM family incl. the cta_group::2 pair-tile kernel, all DiT linears)", "achieved": gemm_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None, "frac_sustained": gemm_tf / peak_sus if peak_sus else None,
                      "peak_sustained": peak_sus, "traffic": traffic, "peak_source": peaks["source"] + ": burst bf16 (= fp16 rate) for `peak`/`frac`, sustained beside it",
-                     "traffic_source": "profile constant: dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/*_gemm_traffic.json), not a live counter",
+                     "traffic_source": "profile constant: dram__bytes_read+write per launch from the latest committed ncu --set full capture (" + os.path.basename(tp) + "), not a live counter",
                      "flops_per_step": fx["gemm"], "launches_per_step": n_cls[0], "ms_per_step": gemm_ms,
                      "share_of_step": gemm_ms / step_ms_prof if step_ms_prof else None},
-        "attention": {"kernel": "attention_tc_kernel (tcgen05 flash attention, S/O in TMEM)", "achieved": attn_tf, "unit": "TFLOP/s", "frac": attn_tf / peak_tf if peak_tf else None, "frac_sustained": attn_tf / peak_sus if peak_sus else None,
+        "attention": {"kernel": "attention_tc_p_kernel (tcgen05 flash attention, S/O in TMEM, software-pipelined softmax warps)", "achieved": attn_tf, "unit": "TFLOP/s", "frac": attn_tf / peak_tf if peak_tf else None, "frac_sustained": attn_tf / peak_sus if peak_sus else None,
                       "ms_per_step": ms_cls[1], "launches_per_step": n_cls[1], "share_of_step": ms_cls[1] / step_ms_prof if step_ms_prof else None},
         "step_breakdown_ms": {"gemm": ms_cls[0], "attention": ms_cls[1], "ln_modulate": ms_cls[2], "gemv_embed": ms_cls[3], "cfg_sampler": ms_cls[4]},
         "step_utilisation": {"F_step_algorithmic": BS * f_step_algorithmic(), "F_step_executed": fx["total"],

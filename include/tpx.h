@@ -193,6 +193,16 @@ int tpx_conv3d_k3(const void* x_f16, const void* W_f16, const void* bias_f16, co
  * ---------------------------------------------------------------------------------------------------------- */
 int tpx_primsdf_query(const float* x_dev, const float* srt_dev, const float* feat_dev, int64_t n, int K, int S, int dim_feat, int inference,
                       float* out_dev, void* stream);
+/* Grid-binned version of the same query (the survey's binned gather, models/primsdf.py:104-109 / inference.py:108-116): a 32^3
+ * grid over the primitives' bounding box holds, per cell, the ascending lists of primitives whose box meets the cell and of the
+ * primitives that can be the nearest centre for a point of the cell; tpx_primsdf_grid_build derives them from srt on the device
+ * (rebuild whenever srt changes), tpx_primsdf_query_grid walks the lists of the point's cell.  Results are identical to
+ * tpx_primsdf_query (same arithmetic in the same order); points outside the grid and over-full lists take the exhaustive loop.
+ * grid_ws: 256-B aligned device memory of tpx_primsdf_grid_bytes(cap_entries) bytes (8 M entries cover the shipped 2048 boxes). */
+size_t tpx_primsdf_grid_bytes(int64_t cap_entries);
+int tpx_primsdf_grid_build(const float* srt_dev, int K, void* grid_ws, size_t grid_bytes, void* stream);
+int tpx_primsdf_query_grid(const float* x_dev, const float* srt_dev, const float* feat_dev, const void* grid_ws, size_t grid_bytes, int64_t n, int K, int S,
+                           int dim_feat, int inference, float* out_dev, void* stream);
 
 /* nn.GELU() (erf form) in place on an fp16 tensor of n elements (n % 8 == 0, 16-B aligned) — the activation of the DINOv2 MLP
  * (models/conditioner/dinov2/layers/mlp.py:33-39); the rest of that encoder is built from the entry points above. */

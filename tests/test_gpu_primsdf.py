@@ -95,3 +95,32 @@ def test_errors_and_empty():
         m(torch.zeros(5, 2).cuda())
     with pytest.raises(_lib.TpxError):
         m(torch.zeros(5, 3))                               # host points: no CPU path
+
+
+@pytest.mark.parametrize("cap", [8 << 20, 2048])
+def test_grid_query_identical_to_exhaustive(cap):
+    """The grid-binned kernel must reproduce the exhaustive one BIT FOR BIT (same visits in the same ascending order, same argmin):
+    points inside and outside the grid's box, covered and uncovered, and a workspace too small for the lists (exhaustive fallback)."""
+    K, S, n = 2048, 8, 20000
+    g = torch.Generator().manual_seed(77)
+    d = torch.randn(K, 3, generator=g)
+    pos = d / d.norm(dim=1, keepdim=True) * (0.55 + 0.1 * torch.rand(K, 1, generator=g))
+    srt = torch.cat([0.03 + 0.05 * torch.rand(K, 1, generator=g), pos], 1).cuda().contiguous()
+    feat = torch.randn(K, 6 * S ** 3, generator=g).cuda()
+    x = (torch.rand(n, 3, generator=g) * 2.6 - 1.3).cuda()          # a share of the points lies outside [-1, 1]^3
+    x[:4000] = (pos[torch.randint(0, K, (4000,), generator=g)] + 0.02 * torch.randn(4000, 3, generator=g)).cuda()   # covered points
+    lib = _lib.lib()
+    ref = torch.empty(n, 6, device="cuda")
+    out = torch.full((n, 6), 7.0, device="cuda")
+    st = _lib.stream_ptr()
+    _lib.check(lib.tpx_primsdf_query(x.data_ptr(), srt.data_ptr(), feat.data_ptr(), n, K, S, 6, 1, ref.data_ptr(), st))
+    nbytes = int(lib.tpx_primsdf_grid_bytes(cap))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.tpx_primsdf_grid_build(srt.data_ptr(), K, ws.data_ptr(), nbytes, st))
+    _lib.check(lib.tpx_primsdf_query_grid(x.data_ptr(), srt.data_ptr(), feat.data_ptr(), ws.data_ptr(), nbytes, n, K, S, 6, 1, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    hdr = ws[:40].view(torch.int32).cpu()      # GridHdr: 5 floats, then total_cover, total_near, overflow, cap, K
+    print("grid lists: cover", int(hdr[5]), "near", int(hdr[6]), "overflow", int(hdr[7]), "cap", int(hdr[8]))
+    assert int(hdr[7]) == (1 if cap == 2048 else 0)
+    assert (ref[:, 0].abs() > 0).float().mean() > 0.5 and (ref[:4000, 1:].abs().sum(1) > 0).float().mean() > 0.9   # the test exercises both branches
+    assert torch.equal(out, ref)

@@ -70,7 +70,7 @@ def kernel_report(tag, what, title):
     hdr, units, rows = raw_table(rep)
     h = {n: i for i, n in enumerate(hdr)}
     recs = []
-    with open(os.path.join(OUT, f"{tag}_{'gemm' if what == 'gemm' else 'attention'}.md"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{ {'gemm': 'gemm', 'attn': 'attention', 'vae': 'vae'}[what] }.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none` — {title}\n\nPer launch (cold cache, ~40 replays; not a timing source):\n\n")
         for r in rows:
             name = re.sub(r"\(CUtensorMap.*", "", r[h["Kernel Name"]]).replace("void ", "")
@@ -102,7 +102,7 @@ def kernel_report(tag, what, title):
                 f.write(f"| {r[sh['# Samples']]} | {100 * int(r[sh['# Samples']]) / tot:.1f}% | `{r[sh['Source']].strip()[:70]}` | {top} |\n")
             mn = collections.Counter()
             for r in body:
-                for m in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "MUFU.EX2", "HMMA"):
+                for m in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM", "STTM", "UTCBAR", "MUFU.EX2", "HMMA"):
                     if m in r[sh["Source"]]:
                         mn[m] += 1
             f.write("\nBlackwell mnemonics present in the captured SASS: " + ", ".join(f"{k}×{v}" for k, v in mn.items()) + "\n")
@@ -114,7 +114,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     agg, tot = launches(tag)
     g = kernel_report(tag, "gemm", "gemm_tc_kernel launches of one DiT block (to_q, proj, qkv, proj, fc1, fc2)")
-    kernel_report(tag, "attn", "attention_tc_kernel (cross- then self-attention of one block)")
+    kernel_report(tag, "attn", "attention_tc_p_kernel (cross- then self-attention of one block)")
+    kernel_report(tag, "vae", "VAE decoder: conv3_halo_kernel / groupnorm_silu_kernel launches of the 8^3 tail (tools/vae_decode_perf.py)")
     if g:
         tr = [to_bytes(*r["dram__bytes_read.sum"]) + to_bytes(*r["dram__bytes_write.sum"]) for r in g if "dram__bytes_read.sum" in r]
         json.dump({"dram_bytes_per_launch": sum(tr) / len(tr), "launches": len(tr), "per_launch": tr,

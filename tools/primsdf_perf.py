@@ -51,8 +51,26 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     cov = float((out["tex"].sum(1) != 0).float().mean())
-    print(f"tpx_primsdf_query: {pts.shape[0]} points x {K} prims  {ms:.2f} ms  {pts.shape[0] / ms / 1e6:.2f} Gpoints/s  "
-          f"({pts.shape[0] * K / ms / 1e9:.2f} T box-tests/s)  covered {cov:.3f}")
+    print(f"PrimSDF.forward (grid-binned query, grid cached): {pts.shape[0]} points x {K} prims  {ms:.2f} ms  {pts.shape[0] / ms / 1e6:.2f} Gpoints/s  covered {cov:.3f}")
+    from tpxl_b200 import _lib
+    lib = _lib.lib()
+    srt_c, feat_c = m.srt_param.data.float().contiguous(), m.feat_param.data.float().contiguous()
+    o2 = torch.empty(pts.shape[0], 6, device="cuda")
+    ws = m._grid[2]
+    hdr = ws[:40].view(torch.int32).cpu()
+    e0.record()
+    for _ in range(5):
+        lib.tpx_primsdf_grid_build(srt_c.data_ptr(), K, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"grid build: {e0.elapsed_time(e1) / 5:.3f} ms  (cover entries {int(hdr[5])}, nearest-candidate entries {int(hdr[6])}, overflow {int(hdr[7])})")
+    e0.record()
+    lib.tpx_primsdf_query(pts.data_ptr(), srt_c.data_ptr(), feat_c.data_ptr(), pts.shape[0], K, S, 6, 1, o2.data_ptr(), _lib.stream_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1)
+    same = bool(torch.equal(o2[:, 0:1], out["sdf"]) and torch.equal(o2[:, 1:4], out["tex"]))
+    print(f"exhaustive tpx_primsdf_query: {ms2:.2f} ms ({pts.shape[0] * K / ms2 / 1e9:.2f} T box-tests/s); identical output: {same}")
     # stock formulation (dense weight matrix per 8192-point chunk) on the same GPU, 64 chunks
     srt_d, feat_d = m.srt_param.data, m.feat_param.data
     chunks = pts[: 64 * 8192].split(8192)
