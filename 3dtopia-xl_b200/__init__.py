@@ -9,11 +9,12 @@ import types
 
 from . import synth  # noqa: F401
 from . import _lib  # noqa: F401
-from . import diffusion, dinov2, dit, pipeline, primsdf, shard, vae  # noqa: F401
+from . import diffusion, dinov2, dit, pipeline, primsdf, ray_marcher, shard, vae  # noqa: F401
 from .diffusion import SpacedDiffusion, create_diffusion  # noqa: F401
 from .dit import DiT  # noqa: F401
 from .pipeline import LatentCodec, PrimXPipeline  # noqa: F401
 from .primsdf import PrimSDF  # noqa: F401
+from .ray_marcher import RayMarcher  # noqa: F401
 from .vae import VAE  # noqa: F401
 
 __version__ = "0.1.0"
@@ -34,3 +35,11 @@ def install() -> None:
     for name, mod in (("dit_crossattn", dit), ("vae3d_dib", vae), ("diffusion", diffusion), ("primsdf", primsdf)):
         sys.modules["models." + name] = mod
         setattr(ref_models, name, mod)
+    # the preview renderer: ``from dva.ray_marcher import RayMarcher`` (inference.py:12) resolves here, so the reference's sm_70
+    # ray-march extensions (dva/mvp/extensions/*) need not be built at all
+    sys.modules["dva.ray_marcher"] = ray_marcher
+    try:
+        import dva as ref_dva
+        setattr(ref_dva, "ray_marcher", ray_marcher)
+    except Exception:
+        pass

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtpx_b200.so")
-SOURCES = ["gemm_tc.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "vae_kernels.cu", "conv_halo.cu", "primsdf.cu", "conditioner.cu", "dit.cu", "vae.cu"]
+SOURCES = ["gemm_tc.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "vae_kernels.cu", "conv_halo.cu", "primsdf.cu", "raymarch.cu", "conditioner.cu", "dit.cu", "vae.cu"]
 HEADERS = ["tpx_common.cuh", "gemm_tc.cuh", "kernels.cuh", os.path.join("..", "..", "include", "tpx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

@@ -61,6 +61,10 @@ int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* be
 int launch_primsdf_query(const float* x, const float* srt, const float* feat, long long n, int K, int S, int dim_feat, int inference, float* out,
                          cudaStream_t st);
 
+// raymarch.cu : ray-march preview (compute_raydirs + mvpraymarch "fixedorder"), rgba [N,H,W,4]
+int launch_raymarch_preview(const float* tpl, const float* primpos, const float* primrot, const float* primscale, const float* campos, const float* camrot,
+                            const float* focal, const float* princpt, int N, int K, int S, int H, int W, float volradius, float stepsize, float fadescale,
+                            float fadeexp, float* out, cudaStream_t st);
 size_t primsdf_grid_bytes(long long cap_entries);
 int launch_primsdf_grid_build(const float* srt, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_primsdf_query_grid(const float* x, const float* srt, const float* feat, const void* ws, size_t ws_bytes, long long n, int K, int S, int dim_feat,

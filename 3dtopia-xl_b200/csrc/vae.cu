@@ -332,6 +332,18 @@ int tpx_primsdf_query(const float* x, const float* srt, const float* feat, int64
     return launch_primsdf_query(x, srt, feat, n, K, S, dim_feat, inference, out, static_cast<cudaStream_t>(stream));
 }
 
+int tpx_raymarch_preview(const float* tpl, const float* primpos, const float* primrot, const float* primscale, const float* campos, const float* camrot,
+                         const float* focal, const float* princpt, int N, int K, int S, int H, int W, float volradius, float stepsize, float fadescale,
+                         float fadeexp, float* rgba_out, void* stream) {
+    TPX_CHECK(tpl != nullptr && primpos != nullptr && primrot != nullptr && primscale != nullptr && campos != nullptr && camrot != nullptr && focal != nullptr &&
+                  princpt != nullptr && rgba_out != nullptr,
+              TPX_ERR_ARG, "raymarch_preview: null argument");
+    int rc = tpx_device_check();
+    if (rc != TPX_OK) return rc;
+    return launch_raymarch_preview(tpl, primpos, primrot, primscale, campos, camrot, focal, princpt, N, K, S, H, W, volradius, stepsize, fadescale, fadeexp, rgba_out,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 size_t tpx_primsdf_grid_bytes(int64_t cap_entries) { return cap_entries > 0 ? primsdf_grid_bytes(cap_entries) : 0; }
 
 int tpx_primsdf_grid_build(const float* srt, int K, void* grid_ws, size_t grid_bytes, void* stream) {

@@ -200,6 +200,20 @@ int tpx_primsdf_query(const float* x_dev, const float* srt_dev, const float* fea
  * tpx_primsdf_query (same arithmetic in the same order); points outside the grid and over-full lists take the exhaustive loop.
  * grid_ws: 256-B aligned device memory of tpx_primsdf_grid_bytes(cap_entries) bytes (8 M entries cover the shipped 2048 boxes). */
 size_t tpx_primsdf_grid_bytes(int64_t cap_entries);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Ray-march preview — RayMarcher.forward (dva/ray_marcher.py:142-229) = compute_raydirs (dva/mvp/extensions/utils/
+ * utils_kernel.cu:15-55) + mvpraymarch(algo 0, usebvh "fixedorder", chlast, maxhitboxes 512, blocksize (8,16))
+ * (dva/mvp/extensions/mvpraymarch/mvpraymarch_subset_kernel.h:14-101): called on every 10th denoising step and for the
+ * turntable (inference.py:349-350).  One batch element per blockIdx.z; all pointers device fp32, contiguous:
+ * template channels-last [N,K,S,S,S,4]; primpos [N,K,3] ALREADY divided by volradius (as the reference passes it),
+ * primrot [N,K,3,3], primscale [N,K,3]; camera as convert_camera_parameters returns it (campos [N,3] in world units,
+ * camrot [N,3,3], focal [N,2] = diagonal of K[:2,:2], princpt [N,2]); pixel (w,h) -> ray through (w,h); stepsize = dt / volradius.
+ * rgba_out [N,H,W,4] (the reference's rayrgba; RayMarcher permutes it to [N,4,H,W]).
+ * ---------------------------------------------------------------------------------------------------------- */
+int tpx_raymarch_preview(const float* template_chlast, const float* primpos, const float* primrot, const float* primscale, const float* campos,
+                         const float* camrot, const float* focal, const float* princpt, int N, int K, int S, int H, int W, float volradius, float stepsize,
+                         float fadescale, float fadeexp, float* rgba_out, void* stream);
 int tpx_primsdf_grid_build(const float* srt_dev, int K, void* grid_ws, size_t grid_bytes, void* stream);
 int tpx_primsdf_query_grid(const float* x_dev, const float* srt_dev, const float* feat_dev, const void* grid_ws, size_t grid_bytes, int64_t n, int K, int S,
                            int dim_feat, int inference, float* out_dev, void* stream);

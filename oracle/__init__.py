@@ -13,4 +13,4 @@ oracle is pinned against fixtures produced by importing the reference's own Pyth
 build container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``; the attention core of
 the un-vendored, unpinned ``xformers`` dependency is restated as softmax(QK^T * Dh^-1/2) V in fp32).
 """
-from . import dit, diffusion, vae, primsdf, dinov2  # noqa: F401
+from . import dit, diffusion, vae, primsdf, dinov2, raymarch  # noqa: F401

@@ -217,3 +217,28 @@ def test_dinov2_encoder_matches_reference(golden_dir):
         assert _rel(blocks[0][0, :8, :16], g["block0_slice"]) < 1e-5 and _rel(blocks[11][0, 5:13, :16], g["block11_slice"]) < 2e-5
         small = np.ascontiguousarray(np.clip(img[:, ::2, ::2][:, :224, :224], 0, 255))
         assert _rel(oracle.dinov2.forward(sd, torch.from_numpy(small))[:, ::24], g["out_small"]) < 2e-5
+
+
+def test_raymarch_restatement_agrees_with_the_reference_torch_marcher():
+    """oracle.raymarch.raymarch (the CUDA kernel's structure: per-warp hit lists, start at the first hit, accumulated steps) against
+    oracle.raymarch.raymarch_dense (the reference's own pure-PyTorch ray-marcher, mvpraymarch.py:391-475): same image up to the
+    step-placement differences of the two formulations (a ray enters a box at most one step apart)."""
+    import torch
+    from oracle import raymarch as rmo
+    g = torch.Generator().manual_seed(11)
+    K, S, H, W, volradius, dt = 12, 4, 16, 16, 50.0, 1.0
+    pos = (torch.rand(K, 3, generator=g) - 0.5) * 0.8
+    scale = 1.0 / (0.15 + 0.1 * torch.rand(K, 1, generator=g)).repeat(1, 3)
+    rot = torch.eye(3)[None].repeat(K, 1, 1)
+    tpl = torch.rand(K, S, S, S, 4, generator=g)
+    tpl[..., :3] *= 255.0
+    tpl[..., 3] *= 20.0
+    RT = torch.tensor([[[1.0, 0, 0, 0], [0, -1.0, 0, 0], [0, 0, -1.0, 3.0 * volradius]]])
+    Kc = torch.tensor([[[1.2 * W, 0, W / 2], [0, 1.2 * W, H / 2], [0, 0, 1.0]]])
+    cam = rmo.convert_camera_parameters(RT, Kc)
+    raypos, raydir, tmm = rmo.compute_raydirs(cam["campos"], cam["camrot"], torch.diagonal(cam["focal"], dim1=1, dim2=2), cam["princpt"], H, W, volradius)
+    a = rmo.raymarch(raypos[0], raydir[0], dt / volradius, tmm[0], tpl, pos, rot, scale)
+    b = rmo.raymarch_dense(raypos[0], raydir[0], dt / volradius, tmm[0], tpl, pos, rot, scale)
+    assert float(b[..., 3].max()) > 0.3
+    rel = float((a - b).norm() / b.norm())
+    assert rel < 2e-2, rel
