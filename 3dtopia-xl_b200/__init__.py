@@ -23,7 +23,7 @@ __version__ = "0.1.0"
 def install() -> None:
     """Make the reference's import paths resolve to this implementation, so ``inference.py`` / ``app.py`` run
     unchanged:  ``models.dit_crossattn`` -> dit, ``models.vae3d_dib`` -> vae, ``models.diffusion`` -> diffusion,
-    ``models.primsdf`` -> primsdf.
+    ``models.primsdf`` -> primsdf, ``models.conditioner.image_dinov2`` -> dinov2, ``dva.ray_marcher`` -> ray_marcher.
     (Equivalent to editing ``class_name`` in configs/inference_dit.yml:32,53; see INTEGRATION.md.)  If the reference's
     ``models`` package is importable it is imported first so its other members (conditioner, primsdf) keep working."""
     try:
@@ -35,6 +35,14 @@ def install() -> None:
     for name, mod in (("dit_crossattn", dit), ("vae3d_dib", vae), ("diffusion", diffusion), ("primsdf", primsdf)):
         sys.modules["models." + name] = mod
         setattr(ref_models, name, mod)
+    # the image conditioner's encoder (configs/inference_dit.yml:49, ``models.conditioner.image_dinov2.Dinov2Wrapper``): the mirror runs
+    # on the tcgen05 GEMM / attention kernels with fp16 tensor-core inputs (9e-4 relative L2 from the reference's fp32 encoder)
+    sys.modules["models.conditioner.image_dinov2"] = dinov2
+    try:
+        import models.conditioner as ref_cond
+        setattr(ref_cond, "image_dinov2", dinov2)
+    except Exception:
+        pass
     # the preview renderer: ``from dva.ray_marcher import RayMarcher`` (inference.py:12) resolves here, so the reference's sm_70
     # ray-march extensions (dva/mvp/extensions/*) need not be built at all
     sys.modules["dva.ray_marcher"] = ray_marcher

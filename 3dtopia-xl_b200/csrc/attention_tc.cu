@@ -1,4 +1,4 @@
-// tcgen05 flash attention for head_dim 72 (padded to 80):  out = softmax(q k^T * scale) v
+// tcgen05 flash attention for head_dim 72 or 64 (padded to 80):  out = softmax(q k^T * scale) v
 //   (contract of xformers.ops.memory_efficient_attention as called at models/attention.py:54,109)
 //
 // One CTA = 256 query rows (two 128-row tiles A/B) of one (batch, head); K / V^T stream through a 2-stage TMA ring
@@ -29,7 +29,7 @@ namespace tpx {
 namespace {
 
 constexpr int TA_DHP = 80;
-constexpr int TA_SUMROW = 72;                           // = Dh: the first padding row of V^T / column of O carries the softmax row sums
+// row Dh of V^T (the first padding row; Dh = 72 or 64) / column Dh of O carries the softmax row sums
 constexpr int TA_BQ = 128, TA_BKV = 128;
 constexpr int TA_Q_BYTES = 128 * 128 + 128 * 32;        // 64-wide SW128 part + 16-wide SW32 part
 constexpr int TA_K_BYTES = TA_Q_BYTES;
@@ -218,7 +218,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         // lands, so column Dh of O accumulates sum_k P[r,k] — rescaled together with O — and the softmax threads carry no sum.
         // Both issuer warps write the same 2 x 128 bytes (row 72 is swizzle row 0: identity chunk order).
         auto write_ones = [&](int s) {
-            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + TA_SUMROW * 128 + lane * 4;
+            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + Dh * 128 + lane * 4;
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + TA_VBOX_BYTES), "r"(0x3C003C00u) : "memory");
             fence_proxy_async();
@@ -436,7 +436,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         uint32_t t2[32];
         tmem_ld_32x16(tO + 64, t2);                  // columns 64..79: the last 8 value columns and, at column Dh, the row sum
         tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float(t2[TA_SUMROW - 64]);
+        const float inv = 1.0f / __uint_as_float((Dh == 64 ? t2[0] : t2[8]));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t t[32];
@@ -602,7 +602,7 @@ attention_tc_p_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
         // lands, so column Dh of O accumulates sum_k P[r,k] — rescaled together with O — and the softmax threads carry no sum.
         // Both issuer warps write the same 2 x 128 bytes (row 72 is swizzle row 0: identity chunk order).
         auto write_ones = [&](int s) {
-            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + TA_SUMROW * 128 + lane * 4;
+            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + Dh * 128 + lane * 4;
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + TA_VBOX_BYTES), "r"(0x3C003C00u) : "memory");
             fence_proxy_async();
@@ -804,7 +804,7 @@ attention_tc_p_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
         uint32_t t2[32];
         tmem_ld_32x16(tO + 64, t2);                  // columns 64..79: the last 8 value columns and, at column Dh, the row sum
         tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float(t2[TA_SUMROW - 64]);
+        const float inv = 1.0f / __uint_as_float((Dh == 64 ? t2[0] : t2[8]));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             uint32_t t[32];
@@ -842,7 +842,7 @@ attention_tc_p_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
                         cudaStream_t st, long long* dbg) {
     TPX_CHECK(B > 0 && H > 0 && Nq > 0 && Nk > 0, TPX_ERR_SHAPE, "attention_tc: empty problem");
-    TPX_CHECK(Dh == TA_SUMROW, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers Dh = 72: 80-wide tiles whose first padding row carries the row sums)", Dh);
+    TPX_CHECK(Dh == 72 || Dh == 64, TPX_ERR_SHAPE, "attention_tc: head dim %d (kernel covers Dh = 72 and 64: 80-wide tiles whose first padding row carries the row sums)", Dh);
     TPX_CHECK(NkPad % 8 == 0 && NkPad >= Nk, TPX_ERR_SHAPE, "attention_tc: NkPad %d must be a multiple of 8 and >= Nk %d", NkPad, Nk);
     TPX_CHECK(H <= 65535 && B <= 65535, TPX_ERR_SHAPE, "attention_tc: grid too large");
     CUtensorMap mQa, mQb, mKa, mKb, mV;

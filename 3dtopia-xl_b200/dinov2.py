@@ -11,7 +11,7 @@ accumulation, like the DiT (10-bit-mantissa inputs, as TF32).  Launch plan per i
     patch embedding   tpx_linear_gated   (pixels / 255 as fp16 [N*1369, 588->640] x W'; Normalize folded into W', b'; accumulates
                                           onto the position embedding already sitting in the token buffer)
     12 x block        tpx_ln_modulate (LayerNorm affine as shift = beta, scale = gamma - 1) -> tpx_linear_heads (qkv, 12 heads x 64,
-                      padded to 80) -> tpx_attention -> tpx_linear_gated (proj, LayerScale as the gate, fp32 residual)
+                      padded to 80, V transposed) -> tpx_attention_tc (tcgen05) -> tpx_linear_gated (proj, LayerScale as the gate, fp32 residual)
                       -> tpx_ln_modulate -> tpx_linear (fc1) -> tpx_gelu_erf -> tpx_linear_gated (fc2, LayerScale)
     final norm        tpx_ln_modulate, then class token + patch tokens are gathered (register tokens dropped)
 """
@@ -148,7 +148,9 @@ class Dinov2Wrapper(nn.Module):
         rows = n * nt
         ln = torch.empty(rows, DIM, dtype=torch.float16, device=dev)
         q = torch.empty(n, HEADS, nt, DHP, dtype=torch.float16, device=dev)
-        k, v = torch.empty_like(q), torch.empty_like(q)
+        k = torch.empty_like(q)
+        ntp = (nt + 7) // 8 * 8
+        vT = torch.zeros(n, HEADS, DHP, ntp, dtype=torch.float16, device=dev)   # V transposed (keys contiguous) for the tcgen05 attention's P V operand
         att = torch.empty(rows, DIM, dtype=torch.float16, device=dev)
         hid = torch.empty(rows, 4 * DIM, dtype=torch.float16, device=dev)
         out16 = torch.empty(rows, DIM, dtype=torch.float16, device=dev)
@@ -163,8 +165,8 @@ class Dinov2Wrapper(nn.Module):
                 _lib.check(lib.tpx_ln_modulate(xr.data_ptr(), rows, DIM, 1e-6, w[f"{i}.ln1.shift"].data_ptr(), w[f"{i}.ln1.scale"].data_ptr(), DIM, rows, 1,
                                                ln.data_ptr(), None, None, 0, st), "norm1")
                 _lib.check(lib.tpx_linear_heads(ln.data_ptr(), DIM, w[f"{i}.attn.qkv.weight"].data_ptr(), w[f"{i}.attn.qkv.bias"].data_ptr(), q.data_ptr(),
-                                                k.data_ptr(), v.data_ptr(), rows, 3 * DIM, DIM, DIM, HEADS, DH, DHP, nt, 1.0, 0, -1, 0, st), "qkv")
-                _lib.check(lib.tpx_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), att.data_ptr(), n, HEADS, nt, nt, DH, DHP, DH ** -0.5, st), "attention")
+                                                k.data_ptr(), vT.data_ptr(), rows, 3 * DIM, DIM, DIM, HEADS, DH, DHP, nt, 1.0, 0, 2, ntp, st), "qkv")
+                _lib.check(lib.tpx_attention_tc(q.data_ptr(), k.data_ptr(), vT.data_ptr(), att.data_ptr(), n, HEADS, nt, nt, ntp, DH, DH ** -0.5, st), "attention")
                 _lib.check(lib.tpx_linear_gated(att.data_ptr(), DIM, w[f"{i}.attn.proj.weight"].data_ptr(), w[f"{i}.attn.proj.bias"].data_ptr(),
                                                 w[f"{i}.ls1"].data_ptr(), DIM, 1, rows, xr.data_ptr(), DIM, rows, DIM, DIM, 0, st), "proj")
                 _lib.check(lib.tpx_ln_modulate(xr.data_ptr(), rows, DIM, 1e-6, w[f"{i}.ln2.shift"].data_ptr(), w[f"{i}.ln2.scale"].data_ptr(), DIM, rows, 1,

@@ -44,10 +44,12 @@ def test_attention_uniform_when_keys_identical():
     assert (out.float() - ref.float()).abs().max() <= 1e-3 * ref.float().abs().max()
 
 
-@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 16, 2048, 2048), (1, 16, 2048, 1370), (1, 2, 256, 128), (2, 3, 300, 77), (1, 4, 128, 1000), (1, 1, 513, 257)])
-def test_attention_tcgen05(B, H, Nq, Nk):
-    """tcgen05 path (Dh 72 -> 80): V given transposed [B,H,80,NkPad]; ragged query and key counts."""
-    Dh, DhP = 72, 80
+@pytest.mark.parametrize("B,H,Nq,Nk,Dh", [(2, 16, 2048, 2048, 72), (1, 16, 2048, 1370, 72), (1, 2, 256, 128, 72), (2, 3, 300, 77, 72), (1, 4, 128, 1000, 72),
+                                           (1, 1, 513, 257, 72), (1, 12, 1374, 1374, 64), (2, 3, 200, 333, 64)])
+def test_attention_tcgen05(B, H, Nq, Nk, Dh):
+    """tcgen05 path (Dh 72 or 64 -> 80-wide tiles): V given transposed [B,H,80,NkPad]; ragged query and key counts; the DINOv2 shape
+    (12 heads x 64, 1374 tokens)."""
+    DhP = 80
     NkPad = (Nk + 7) // 8 * 8
     g = torch.Generator(device="cuda").manual_seed(Nq * 7 + Nk)
     def mk(n):
