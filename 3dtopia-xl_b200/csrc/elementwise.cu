@@ -14,47 +14,21 @@ namespace tpx {
 constexpr int LN_MAX_ITERS = 16;  // D <= 2048
 
 template <int NI>   // NI = D / 128 float4 per lane: the row lives in exactly NI*4 registers
-__global__ void __launch_bounds__(256, NI <= 9 ? 4 : (NI <= 12 ? 3 : 2)) ln_modulate_kernel(float* __restrict__ x, int rows, float eps, const __half* __restrict__ shift,
+__global__ void __launch_bounds__(256) ln_modulate_kernel(float* __restrict__ x, int rows, float eps, const __half* __restrict__ shift,
                                                           const __half* __restrict__ scale, int mod_bstride, int rows_per_batch, int mod_batches,
                                                           __half* __restrict__ out, const __half* __restrict__ pre_gate,
                                                           const __half* __restrict__ pre_const, int pre_row0) {
     constexpr int D = NI * 128;
-    // The block's modulation vectors go to shared memory while the rows are in flight (the adaLN table was written by an earlier
-    // kernel of this forward, so it may be read before griddepcontrol.wait only if that kernel is not the direct predecessor —
-    // it is not guaranteed: stage after the wait).  One memory latency per row instead of two.
-    __shared__ __align__(16) __half s_mod[2][D];
     pdl_launch_dependents();
     pdl_wait();
-    const int row_first = blockIdx.x * (blockDim.x >> 5);
-    const int row = row_first + (threadIdx.x >> 5);
-    const int row_last = min(row_first + static_cast<int>(blockDim.x >> 5), rows) - 1;
-    const int bm_first = (row_first / rows_per_batch) % mod_batches;
-    const bool mod_in_smem = bm_first == (row_last / rows_per_batch) % mod_batches;      // block-uniform
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    const bool active = row < rows;
-    const int bm = active ? (row / rows_per_batch) % mod_batches : 0;
-    if (!active) {                                    // (tail block) still helps staging, then leaves
-        if (mod_in_smem) {
-            for (int c = threadIdx.x * 8; c < 2 * D; c += blockDim.x * 8) {
-                const int which = c >= D ? 1 : 0, cc = c - which * D;
-                const __half* src = (which ? scale : shift) + static_cast<size_t>(bm_first) * mod_bstride + cc;
-                *reinterpret_cast<uint4*>(&s_mod[which][cc]) = __ldg(reinterpret_cast<const uint4*>(src));
-            }
-        }
-        __syncthreads();
-        return;
-    }
+    const int bm = (row / rows_per_batch) % mod_batches;
     float4 v[NI];
     float* xr = x + static_cast<size_t>(row) * D;
 #pragma unroll
     for (int i = 0; i < NI; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
-    if (mod_in_smem) {                                // issued behind the row loads: both are in flight together
-        for (int c = threadIdx.x * 8; c < 2 * D; c += blockDim.x * 8) {
-            const int which = c >= D ? 1 : 0, cc = c - which * D;
-            const __half* src = (which ? scale : shift) + static_cast<size_t>(bm_first) * mod_bstride + cc;
-            *reinterpret_cast<uint4*>(&s_mod[which][cc]) = __ldg(reinterpret_cast<const uint4*>(src));
-        }
-    }
     if (pre_gate != nullptr && row >= pre_row0) {
         const __half* gp = pre_gate + static_cast<size_t>(bm) * mod_bstride;
 #pragma unroll
@@ -80,15 +54,13 @@ __global__ void __launch_bounds__(256, NI <= 9 ? 4 : (NI <= 12 ? 3 : 2)) ln_modu
         q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-    __syncthreads();                                  // s_mod complete (every warp of the block reaches this exactly once)
     const __half* shp = shift + static_cast<size_t>(bm) * mod_bstride;
     const __half* scp = scale + static_cast<size_t>(bm) * mod_bstride;
     __half* orow = out + static_cast<size_t>(row) * D;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
         const int c = (lane + 32 * i) * 4;
-        const uint2 shv = mod_in_smem ? *reinterpret_cast<const uint2*>(&s_mod[0][c]) : __ldg(reinterpret_cast<const uint2*>(shp + c));
-        const uint2 scv = mod_in_smem ? *reinterpret_cast<const uint2*>(&s_mod[1][c]) : __ldg(reinterpret_cast<const uint2*>(scp + c));
+        const uint2 shv = __ldg(reinterpret_cast<const uint2*>(shp + c)), scv = __ldg(reinterpret_cast<const uint2*>(scp + c));
         const __half2 sh0 = *reinterpret_cast<const __half2*>(&shv.x), sh1 = *reinterpret_cast<const __half2*>(&shv.y);
         const __half2 sc0 = *reinterpret_cast<const __half2*>(&scv.x), sc1 = *reinterpret_cast<const __half2*>(&scv.y);
         const float m0 = h2f_round(1.0f + __low2float(sc0)), m1 = h2f_round(1.0f + __high2float(sc0));
