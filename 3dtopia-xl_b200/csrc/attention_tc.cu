@@ -837,757 +837,6 @@ attention_tc_p_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
 }
 
 
-// =====================================================================================================================
-// Variant 2: P in TENSOR MEMORY.  The fp16 probabilities of a tile overwrite the first 64 columns of their own score tile
-// (tcgen05.st, thread == row == TMEM lane: no swizzle arithmetic, no shared-memory stores, no proxy fence) and the P V MMAs take
-// their A operand from TMEM.  Because P aliases S, Q K^T(j+1) of a query tile is issued right after P V(j) (the tensor pipe
-// executes in issue order), so a softmax warpgroup waits for its own MMAs once per tile — and the OTHER warpgroup has the MUFU to
-// itself during that wait: the two query tiles alternate on the exponential unit instead of sharing it.  The 64 KB of P buffers
-// become a fourth K/V stage.
-constexpr int TT_KV_STAGES = 4;
-constexpr int TT_OFF_BAR = TA_OFF_KV + TT_KV_STAGES * TA_KV_STAGE;
-constexpr int TT_SMEM = TT_OFF_BAR + 256 + 1024;
-static_assert(TT_SMEM <= 232448, "attention (TMEM P): shared memory budget");
-
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
-__global__ void __launch_bounds__(TA_THREADS, 1)
-attention_tc_t_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
-                      const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                      int Dh, float scale_log2, long long* __restrict__ dbg, unsigned stagger_cycles, int flags) {
-    extern __shared__ __align__(1024) uint8_t ta_smem_raw[];
-    uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TT_OFF_BAR);
-    uint64_t* q_full = bars;            // 1
-    uint64_t* kv_full = bars + 1;       // TT_KV_STAGES
-    uint64_t* kv_empty = bars + 5;      // TT_KV_STAGES
-    uint64_t* s_full = bars + 9;        // 2 (per query tile)
-    uint64_t* p_full = bars + 11;       // 2
-    uint64_t* o_full = bars + 13;       // 2
-    uint64_t* tok = bars + 15;          // 2 x 4: MUFU hand-over between the two softmax warps of a sub-partition (flags & 2)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (2 * TA_BQ);
-    const int h = blockIdx.y, b = blockIdx.z;
-    const int bh = b * H + h;
-    const int nkt = (Nk + TA_BKV - 1) / TA_BKV;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQa); tma_prefetch_desc(&tmQb); tma_prefetch_desc(&tmKa); tma_prefetch_desc(&tmKb); tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1 && lane == 0) {
-        mbar_init(q_full, 1);
-        for (int i = 0; i < TT_KV_STAGES; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 2);      // one commit from each of the two MMA issuer warps
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
-            mbar_init(&o_full[i], 1);
-        }
-        for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
-    // TMEM columns: S_A [0,128) (P_A = fp16 pairs in [0,64))  S_B [128,256) (P_B in [128,192))  O_A [256,336)  O_B [384,464)
-
-    if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, 2 * TA_Q_BYTES);
-            for (int X = 0; X < 2; ++X) {
-                uint8_t* qs = smem + TA_OFF_Q + X * TA_Q_BYTES;
-                const int row = bh * Nq + q0 + X * TA_BQ;
-                tma_load_2d(qs, &tmQa, q_full, 0, row);
-                tma_load_2d(qs + 128 * 128, &tmQb, q_full, 64, row);
-            }
-        }
-        __syncwarp();
-        for (int j = 0; j < nkt; ++j) {
-            const int s = j % TT_KV_STAGES;
-            mbar_wait(&kv_empty[s], ((j / TT_KV_STAGES) & 1) ^ 1);
-            if (elect_one()) {
-                uint8_t* ks = smem + TA_OFF_KV + s * TA_KV_STAGE;
-                uint8_t* vs = ks + TA_K_BYTES;
-                mbar_arrive_expect_tx(&kv_full[s], TA_KV_STAGE);
-                const int krow = bh * Nk + j * TA_BKV;
-                tma_load_2d(ks, &tmKa, &kv_full[s], 0, krow);
-                tma_load_2d(ks + 128 * 128, &tmKb, &kv_full[s], 64, krow);
-                tma_load_2d(vs, &tmV, &kv_full[s], j * TA_BKV, bh * TA_DHP);
-                tma_load_2d(vs + TA_VBOX_BYTES, &tmV, &kv_full[s], j * TA_BKV + 64, bh * TA_DHP);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1 || warp == 3) {
-        // one issuer warp per query tile (uniform control flow, one elected lane issues)
-        const int X = warp == 1 ? 0 : 1;
-        constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
-        constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
-        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t ts = tbase + X * 128, to = tbase + 256 + X * 128;
-        auto issue_qk = [&](int s) {
-            const uint32_t qa = sbase + TA_OFF_Q + X * TA_Q_BYTES, ka = sbase + TA_OFF_KV + s * TA_KV_STAGE;
-            const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
-            const uint64_t dq2 = umma_desc_kmajor<32>(qa + 128 * 128), dk2 = umma_desc_kmajor<32>(ka + 128 * 128);
-            if (elect_one()) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) umma_f16(ts, dq + 2 * i, dk + 2 * i, idesc_qk, i > 0 ? 1u : 0u);
-                umma_f16(ts, dq2, dk2, idesc_qk, 1u);
-                umma_commit(&s_full[X]);
-            }
-            __syncwarp();
-        };
-        // O_X += P V: A = P from tensor memory (row == lane, 8 columns of fp16 pairs per 16 keys), B = V^T tile from shared memory
-        auto issue_pv = [&](int s, uint32_t acc_first) {
-            const uint32_t va = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES;
-            const uint64_t dv0 = umma_desc_kmajor<128>(va), dv1 = umma_desc_kmajor<128>(va + TA_VBOX_BYTES);
-            if (elect_one()) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) umma_f16_ts(to, ts + 8 * i, dv0 + 2 * i, idesc_pv, i != 0 ? 1u : acc_first);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) umma_f16_ts(to, ts + 32 + 8 * i, dv1 + 2 * i, idesc_pv, 1u);
-                umma_commit(&kv_empty[s]);
-            }
-            __syncwarp();
-        };
-        auto write_ones = [&](int s) {       // row Dh of the V^T tile := 1 -> column Dh of O carries the row sums
-            const uint32_t a = sbase + TA_OFF_KV + s * TA_KV_STAGE + TA_K_BYTES + Dh * 128 + lane * 4;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + TA_VBOX_BYTES), "r"(0x3C003C00u) : "memory");
-            fence_proxy_async();
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
-        write_ones(0);
-        tc_fence_after();
-        issue_qk(0);
-        for (int j = 0; j < nkt; ++j) {
-            const int s = j % TT_KV_STAGES, sn = (j + 1) % TT_KV_STAGES;
-            if (j + 1 < nkt) {
-                mbar_wait(&kv_full[sn], ((j + 1) / TT_KV_STAGES) & 1);
-                write_ones(sn);
-            }
-            mbar_wait(&p_full[X], j & 1);
-            tc_fence_after();
-            issue_pv(s, j > 0 ? 1u : 0u);
-            if (j + 1 < nkt) issue_qk(sn);       // overwrites S_X / P_X: ordered behind P V(j) by the in-order tensor pipe
-        }
-        if (elect_one()) umma_commit(&o_full[X]);
-        __syncwarp();
-    }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        const int X = (warp - 4) >> 2;               // query tile of this warpgroup
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;              // row in the tile == TMEM lane
-        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tS = tmem_base + X * 128 + lane_off;
-        const uint32_t tO = tmem_base + 256 + X * 128 + lane_off;
-        float m_ref = 0.f;
-        const bool stale_max = (flags & 1) != 0;
-        const bool use_tok = (flags & 2) != 0;
-        // strict alternation A, B, A, B ... of the exponential phases of the two warps that share a sub-partition's MUFU
-        auto tok_acquire = [&](int j) {
-            if (!use_tok) return;
-            if (X == 0) { if (j > 0) mbar_wait(&tok[quad], (j - 1) & 1); }
-            else mbar_wait(&tok[4 + quad], j & 1);
-        };
-        auto tok_release = [&]() {
-            if (!use_tok) return;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tok[(X == 0 ? 4 : 0) + quad]);
-        };
-        auto rescale_o = [&](bool need, float mx) {
-            const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
-            if (need) m_ref = mx;
-            uint32_t t[32];
-            tmem_ld_32x32(tO, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x32(tO, t);
-            tmem_ld_32x32(tO + 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x32(tO + 32, t);
-            tmem_ld_32x16(tO + 64, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x16(tO + 64, t);
-            tmem_st_wait();
-        };
-        auto exp_chunk = [&](const uint32_t* sc, float msc, uint32_t (&pk)[16], bool track, float& m0, float& m1) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float s0 = __uint_as_float(sc[i]), s1 = __uint_as_float(sc[i + 1]);
-                const float s2 = __uint_as_float(sc[i + 2]), s3 = __uint_as_float(sc[i + 3]);
-                if (track) { m0 = fmaxf(m0, fmaxf(s0, s2)); m1 = fmaxf(m1, fmaxf(s1, s3)); }
-                const float p0 = ex2(fmaf(s0, scale_log2, -msc)), p1 = ex2(fmaf(s1, scale_log2, -msc));
-                const float p2 = ex2(fmaf(s2, scale_log2, -msc)), p3 = ex2(fmaf(s3, scale_log2, -msc));
-                __half2 ha = __floats2half2_rn(p0, p1), hb = __floats2half2_rn(p2, p3);
-                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&ha);
-                pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hb);
-            }
-        };
-        if (X == 1 && stagger_cycles != 0) {
-            const long long t_end = clock64() + stagger_cycles;
-            while (clock64() < t_end) {}
-        }
-        for (int j = 0; j < nkt; ++j) {
-            const int nvalid = Nk - j * TA_BKV;      // keys of this tile that exist (>= 1)
-            if (r == 0) TA_DBG(X, 1);
-            mbar_wait(&s_full[X], j & 1);            // Q K^T(j) done — and with it P V(j-1): O_X is quiescent, P_X(j-1) consumed
-            tc_fence_after();
-            if (r == 0) TA_DBG(X, 2);
-            uint32_t sv[128];
-            tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-            tmem_ld_wait();
-            tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));     // land under the first chunk's exponentials
-            tmem_ld_32x32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(sv[64]));
-            tmem_ld_32x32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(sv[96]));
-            if (r == 0) TA_DBG(X, 3);
-            const bool fast = j > 0 && nvalid >= TA_BKV && stale_max;
-            if (fast) {
-                const float msc = m_ref * scale_log2;
-                float m0 = -INFINITY, m1 = -INFINITY;
-                uint32_t pk[16];
-                tok_acquire(j);
-                if (r == 0) TA_DBG(X, 5);
-                exp_chunk(&sv[0], msc, pk, true, m0, m1);
-                tmem_ld_wait();                                  // the whole score row is in registers: its columns may take P
-                tmem_st_16(tS, pk);
-                exp_chunk(&sv[32], msc, pk, true, m0, m1);
-                tmem_st_16(tS + 16, pk);
-                exp_chunk(&sv[64], msc, pk, true, m0, m1);
-                tmem_st_16(tS + 32, pk);
-                exp_chunk(&sv[96], msc, pk, true, m0, m1);
-                tok_release();
-                tmem_st_16(tS + 48, pk);
-                const float mx = fmaxf(m0, m1);
-                const bool need = (mx - m_ref) * scale_log2 > 8.0f;
-                if (__any_sync(0xffffffffu, need)) {             // rare: redo this tile against the new maximum
-                    tmem_st_wait();
-                    rescale_o(need, mx);
-                    const float msc2 = m_ref * scale_log2;
-                    float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        exp_chunk(&sv[c * 32], msc2, pk, false, d0, d1);
-                        tmem_st_16(tS + 16 * c, pk);
-                    }
-                }
-            } else {
-                // first tile, ragged last tile (or stale_max off): maximum first, then the exponentials
-                tmem_ld_wait();
-                tok_acquire(j);
-                if (r == 0) TA_DBG(X, 5);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
-                if (j == 0) {
-                    m_ref = mx;
-                } else {
-                    const bool need = (mx - m_ref) * scale_log2 > 8.0f;
-                    if (__any_sync(0xffffffffu, need)) rescale_o(need, mx);
-                }
-                const float msc = m_ref * scale_log2;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
-                        float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
-                        if (c * 32 + i >= nvalid) p0 = 0.f;
-                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    tmem_st_16(tS + 16 * c, pk);
-                }
-                tok_release();
-            }
-            if (r == 0) TA_DBG(X, 6);
-            tmem_st_wait();                 // P is in tensor memory
-            tc_fence_before();
-            mbar_arrive(&p_full[X]);
-            if (r == 0) TA_DBG(X, 7);
-        }
-        mbar_wait(&o_full[X], 0);
-        tc_fence_after();
-        const int row = q0 + X * TA_BQ + r;
-        __half* orow = out + (static_cast<size_t>(b) * Nq + (row < Nq ? row : 0)) * (H * Dh) + h * Dh;
-        uint32_t t2[32];
-        tmem_ld_32x16(tO + 64, t2);                  // columns 64..79: the last 8 value columns and, at column Dh, the row sum
-        tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float((Dh == 64 ? t2[0] : t2[8]));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            uint32_t t[32];
-            if (c < 2) {
-                tmem_ld_32x32(tO + c * 32, t);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = t2[i];
-            }
-#pragma unroll
-            for (int d8 = 0; d8 < (c < 2 ? 32 : 16); d8 += 8) {
-                const int d = c * 32 + d8;
-                if (row < Nq && d < Dh) {
-                    Pack8 v;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn(__uint_as_float(t[d8 + i]) * inv);
-                    *reinterpret_cast<uint4*>(orow + d) = v.u;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        __syncwarp();
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-
-// =====================================================================================================================
-// Variant 3: THREE softmax warpgroups per CTA.  The exponential unit of a sub-partition serves one MUFU.EX2 per ~9 cycles when two
-// or more warps feed it, but a warp spends ~1 000-1 500 cycles per tile in fixed latencies (barrier polls, tcgen05.ld, fence,
-// arrives); with two warps per sub-partition (variants 0-2) the unit idles ~35 % of the time whatever is hidden or split.  Here a
-// CTA owns ONE 128-row query tile and its key range is dealt out in 64-key tiles to three warpgroups (tile j -> warpgroup j % 3),
-// each with a private score tile S_w (64 TMEM columns), a private un-normalised accumulator O_w (80 columns) and a private running
-// maximum, so the three never synchronise inside the key loop: three warps per sub-partition keep the MUFU fed.  At the end the
-// three partial results are merged like split-K flash decoding:  out = sum_w 2^(m_w - M) O_w / sum_w 2^(m_w - M) l_w.
-//   warp 0: TMA producer (+ TMEM allocation); warps 1-3: MMA issuers of warpgroups 0-2; warps 4-15: softmax, one thread per row.
-constexpr int T3_BKV = 64;
-constexpr int T3_K_BYTES = 64 * 128 + 64 * 32;           // 64 keys: 64-wide SW128 part + 16-wide SW32 part
-constexpr int T3_V_BYTES = TA_DHP * 128;                  // 80 rows x 64 keys
-constexpr int T3_NK = 7, T3_NV = 8;                       // K and V^T tiles ride separate rings: a K slot is released by its Q K^T,
-                                                          // a V slot by its P V a whole round later
-constexpr int T3_P_BYTES = 128 * 128;                     // 128 rows x 64 keys fp16
-constexpr int T3_OFF_Q = 0;
-constexpr int T3_OFF_P = TA_Q_BYTES;
-constexpr int T3_OFF_K = T3_OFF_P + 3 * T3_P_BYTES;
-constexpr int T3_OFF_V = T3_OFF_K + T3_NK * T3_K_BYTES;
-constexpr int T3_OFF_BAR = T3_OFF_V + T3_NV * T3_V_BYTES;
-constexpr int T3_SMEM = T3_OFF_BAR + 512 + 1024;
-constexpr int T3_THREADS = 512;
-constexpr int T3_MERGE_LD = 75;                           // floats per row of the merge buffers (odd: conflict-free thread-per-row access)
-static_assert(T3_SMEM <= 232448, "attention (3 warpgroups): shared memory budget");
-static_assert(T3_K_BYTES % 1024 == 0 && T3_V_BYTES % 1024 == 0 && T3_OFF_K % 1024 == 0, "operand tiles must stay 1024-B aligned");
-static_assert(3 * 128 * T3_MERGE_LD * 4 <= T3_NK * T3_K_BYTES + T3_NV * T3_V_BYTES, "merge buffers live in the drained K/V rings");
-
-// lane 0's view of a barrier phase, broadcast (a completed phase stays completed until this warp itself moves on)
-__device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity) {
-    return __shfl_sync(0xffffffffu, mbar_try_wait(bar, parity) ? 1 : 0, 0) != 0;
-}
-
-__global__ void __launch_bounds__(T3_THREADS, 1)
-attention_tc_3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKa,
-                      const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, int H, int Nq, int Nk,
-                      int Dh, float scale_log2, long long* __restrict__ dbg, int flags) {
-    extern __shared__ __align__(1024) uint8_t ta_smem_raw[];
-    uint8_t* smem = ta_smem_raw + ((1024u - (smem_u32(ta_smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T3_OFF_BAR);
-    uint64_t* q_full = bars;                  // 1
-    uint64_t* k_full = bars + 1;              // T3_NK
-    uint64_t* k_empty = bars + 9;             // T3_NK
-    uint64_t* v_full = bars + 17;             // T3_NV
-    uint64_t* v_empty = bars + 25;            // T3_NV
-    uint64_t* s_full = bars + 33;             // 3 (per warpgroup)
-    uint64_t* s_free = bars + 36;             // 3
-    uint64_t* p_full = bars + 39;             // 3
-    uint64_t* o_full = bars + 42;             // 3
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 45);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * TA_BQ;
-    const int h = blockIdx.y, b = blockIdx.z;
-    const int bh = b * H + h;
-    const int nkt = (Nk + T3_BKV - 1) / T3_BKV;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQa); tma_prefetch_desc(&tmQb); tma_prefetch_desc(&tmKa); tma_prefetch_desc(&tmKb); tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1 && lane == 0) {
-        mbar_init(q_full, 1);
-        for (int i = 0; i < T3_NK; ++i) {
-            mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);       // a slot belongs to one tile, i.e. one warpgroup's issuer
-        }
-        for (int i = 0; i < T3_NV; ++i) {
-            mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
-        }
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&s_free[i], 128);
-            mbar_init(&p_full[i], 128);
-            mbar_init(&o_full[i], 1);
-        }
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
-    // TMEM columns: S_w at 64 w (w = 0..2), O_w at 192 + 96 w (80 wide)
-
-    // 4 control warps x 64 + 12 softmax warps x 144 registers = 63 488 <= 65 536 (ptxas sizes each branch to its setmaxnreg value)
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, TA_Q_BYTES);
-            const int row = bh * Nq + q0;
-            tma_load_2d(smem + T3_OFF_Q, &tmQa, q_full, 0, row);
-            tma_load_2d(smem + T3_OFF_Q + 128 * 128, &tmQb, q_full, 64, row);
-        }
-        __syncwarp();
-        // K and V^T tiles run ahead independently, each as far as its ring allows (one thread, two streams: poll, never block)
-        int jk = 0, jv = 0;
-        long long t0 = clock64();
-        while (jk < nkt || jv < nkt) {
-            bool progress = false;
-            if (jk < nkt && mbar_poll(&k_empty[jk % T3_NK], ((jk / T3_NK) & 1) ^ 1)) {
-                if (elect_one()) {
-                    uint8_t* ks = smem + T3_OFF_K + (jk % T3_NK) * T3_K_BYTES;
-                    mbar_arrive_expect_tx(&k_full[jk % T3_NK], T3_K_BYTES);
-                    const int krow = bh * Nk + jk * T3_BKV;
-                    tma_load_2d(ks, &tmKa, &k_full[jk % T3_NK], 0, krow);
-                    tma_load_2d(ks + 64 * 128, &tmKb, &k_full[jk % T3_NK], 64, krow);
-                }
-                __syncwarp();
-                ++jk;
-                progress = true;
-            }
-            if (jv < nkt && mbar_poll(&v_empty[jv % T3_NV], ((jv / T3_NV) & 1) ^ 1)) {
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&v_full[jv % T3_NV], T3_V_BYTES);
-                    tma_load_2d(smem + T3_OFF_V + (jv % T3_NV) * T3_V_BYTES, &tmV, &v_full[jv % T3_NV], jv * T3_BKV, bh * TA_DHP);
-                }
-                __syncwarp();
-                ++jv;
-                progress = true;
-            }
-            if (progress) { t0 = clock64(); continue; }
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000LL) { if (lane == 0) printf("tpx: attention producer timeout block %d jk %d jv %d\n", blockIdx.x, jk, jv); __trap(); }
-        }
-    } else if (warp < 4) {
-        const int w = warp - 1;                       // issuer of warpgroup w: tiles j = w, w+3, ...
-        const int nt = nkt > w ? (nkt - w + 2) / 3 : 0;
-        constexpr uint32_t idesc_qk = umma_idesc_f16(128, T3_BKV);
-        constexpr uint32_t idesc_pv = umma_idesc_f16(128, TA_DHP);
-        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t ts = tbase + 64 * w, to = tbase + 192 + 96 * w;
-        const uint32_t qa = sbase + T3_OFF_Q, pa = sbase + T3_OFF_P + w * T3_P_BYTES;
-        auto issue_qk = [&](int j) {                  // S_w = Q K(j)^T, then the K slot is free again
-            const int ks = j % T3_NK;
-            const uint32_t ka = sbase + T3_OFF_K + ks * T3_K_BYTES;
-            const uint64_t dq = umma_desc_kmajor<128>(qa), dk = umma_desc_kmajor<128>(ka);
-            const uint64_t dq2 = umma_desc_kmajor<32>(qa + 128 * 128), dk2 = umma_desc_kmajor<32>(ka + 64 * 128);
-            if (elect_one()) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) umma_f16(ts, dq + 2 * i, dk + 2 * i, idesc_qk, i > 0 ? 1u : 0u);
-                umma_f16(ts, dq2, dk2, idesc_qk, 1u);
-                umma_commit(&s_full[w]);
-                umma_commit(&k_empty[ks]);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int j, uint32_t acc_first) {
-            const int vs = j % T3_NV;
-            const uint32_t va = sbase + T3_OFF_V + vs * T3_V_BYTES;
-            const uint64_t dp = umma_desc_kmajor<128>(pa), dv = umma_desc_kmajor<128>(va);
-            if (elect_one()) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) umma_f16(to, dp + 2 * i, dv + 2 * i, idesc_pv, i != 0 ? 1u : acc_first);
-                umma_commit(&v_empty[vs]);
-                umma_commit(&o_full[w]);
-            }
-            __syncwarp();
-        };
-        auto write_ones = [&](int j) {                // row Dh of the V^T tile := 1 -> column Dh of O_w carries the row sums
-            const uint32_t a = sbase + T3_OFF_V + (j % T3_NV) * T3_V_BYTES + Dh * 128 + lane * 4;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(0x3C003C00u) : "memory");
-            fence_proxy_async();
-            __syncwarp();
-        };
-        if (nt > 0) {
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[w % T3_NK], 0);
-            tc_fence_after();
-            issue_qk(w);
-            for (int t = 0; t < nt; ++t) {
-                const int j = w + 3 * t, jn = j + 3;
-                // whichever is ready first: the next tile's Q K^T (its keys have landed and the warpgroup has pulled S_w(t) into
-                // registers) or this tile's P V (its V^T tile has landed, the ones row is written, P_w(t) is complete)
-                bool need_qk = t + 1 < nt, need_pv = true, ones = false;
-                long long t0 = clock64();
-                while (need_qk || need_pv) {
-                    bool progress = false;
-                    if (need_qk && mbar_poll(&s_free[w], t & 1) && mbar_poll(&k_full[jn % T3_NK], (jn / T3_NK) & 1)) {
-                        tc_fence_after();
-                        issue_qk(jn);
-                        need_qk = false;
-                        progress = true;
-                    }
-                    if (!ones && mbar_poll(&v_full[j % T3_NV], (j / T3_NV) & 1)) {
-                        write_ones(j);
-                        ones = true;
-                        progress = true;
-                    }
-                    if (need_pv && ones && mbar_poll(&p_full[w], t & 1)) {
-                        tc_fence_after();
-                        issue_pv(j, t > 0 ? 1u : 0u);
-                        need_pv = false;
-                        progress = true;
-                    }
-                    if (progress) continue;
-                    __nanosleep(32);
-                    if (clock64() - t0 > 4000000000LL) { if (lane == 0) printf("tpx: attention issuer timeout block %d wg %d tile %d qk %d pv %d ones %d\n", blockIdx.x, w, t, (int)need_qk, (int)need_pv, (int)ones); __trap(); }
-                }
-            }
-        }
-    } else {
-        const int w = (warp - 4) >> 2;                // warpgroup
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;               // row in the tile == TMEM lane
-        const int nt = nkt > w ? (nkt - w + 2) / 3 : 0;
-        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tS = tmem_base + 64 * w + lane_off;
-        const uint32_t tO = tmem_base + 192 + 96 * w + lane_off;
-        const uint32_t pS = smem_u32(smem) + T3_OFF_P + w * T3_P_BYTES + r * 128;   // shared-window address of this row of P
-        const int sw = r & 7;
-        float m_ref = -INFINITY;
-        const bool stale_max = (flags & 1) != 0;
-        auto rescale_o = [&](bool need, float mx) {
-            const float a = need ? ex2((m_ref - mx) * scale_log2) : 1.0f;
-            if (need) m_ref = mx;
-            uint32_t t[32];
-            tmem_ld_32x32(tO, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x32(tO, t);
-            tmem_ld_32x32(tO + 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x32(tO + 32, t);
-            tmem_ld_32x16(tO + 64, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
-            tmem_st_32x16(tO + 64, t);
-            tmem_st_wait();
-        };
-        auto exp_chunk = [&](const uint32_t* sc, float msc, uint32_t (&pk)[16], bool track, float& m0, float& m1) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float s0 = __uint_as_float(sc[i]), s1 = __uint_as_float(sc[i + 1]);
-                const float s2 = __uint_as_float(sc[i + 2]), s3 = __uint_as_float(sc[i + 3]);
-                if (track) { m0 = fmaxf(m0, fmaxf(s0, s2)); m1 = fmaxf(m1, fmaxf(s1, s3)); }
-                const float p0 = ex2(fmaf(s0, scale_log2, -msc)), p1 = ex2(fmaf(s1, scale_log2, -msc));
-                const float p2 = ex2(fmaf(s2, scale_log2, -msc)), p3 = ex2(fmaf(s3, scale_log2, -msc));
-                __half2 ha = __floats2half2_rn(p0, p1), hb = __floats2half2_rn(p2, p3);
-                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&ha);
-                pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hb);
-            }
-        };
-        auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {      // chunk c = 32 keys = four 16-byte pieces of the 128-byte row
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pS + (((c * 4 + q) ^ sw) << 4)), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                             "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                             : "memory");
-        };
-        for (int t = 0; t < nt; ++t) {
-            const int nvalid = Nk - (w + 3 * t) * T3_BKV;      // keys of this tile that exist (>= 1)
-            if (r == 0) TA_DBG(w, 1);
-            mbar_wait(&s_full[w], t & 1);
-            tc_fence_after();
-            if (r == 0) TA_DBG(w, 2);
-            uint32_t sv[64];
-            tmem_ld_32x32(tS, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-            tmem_ld_32x32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&s_free[w]);                           // the score row is in registers: S_w may take Q K^T of the next tile
-            if (r == 0) TA_DBG(w, 3);
-            // row maximum first (32 FMNMX3): in the common case it only confirms the stale reference, and no score has to stay live
-            // past its exponential for a redo
-            float mx;
-            if (nvalid >= T3_BKV) {
-                float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    m0 = fmaxf(m0, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 2])));
-                    m1 = fmaxf(m1, fmaxf(__uint_as_float(sv[i + 1]), __uint_as_float(sv[i + 3])));
-                }
-                mx = fmaxf(m0, m1);
-            } else {
-                mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 64; ++i)
-                    if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
-            }
-            if (t > 0) {
-                mbar_wait(&o_full[w], (t - 1) & 1);            // previous P V retired (a whole round ago): P_w is free, O_w quiescent
-                tc_fence_after();
-                const bool need = stale_max ? (mx - m_ref) * scale_log2 > 8.0f : mx > m_ref;
-                if (__any_sync(0xffffffffu, need)) rescale_o(need, mx);     // rare with the stale reference
-            } else {
-                m_ref = mx;
-            }
-            if (r == 0) TA_DBG(w, 5);
-            const float msc = m_ref * scale_log2;
-            uint32_t pk[16];
-            if (nvalid >= T3_BKV) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
-                        const float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    store_chunk(c, pk);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float p0 = ex2(fmaf(__uint_as_float(sv[c * 32 + i]), scale_log2, -msc));
-                        float p1 = ex2(fmaf(__uint_as_float(sv[c * 32 + i + 1]), scale_log2, -msc));
-                        if (c * 32 + i >= nvalid) p0 = 0.f;
-                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    store_chunk(c, pk);
-                }
-            }
-            if (r == 0) TA_DBG(w, 6);
-            fence_proxy_async();            // make the P stores visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(&p_full[w]);
-            if (r == 0) TA_DBG(w, 7);
-        }
-        // ---- merge of the three partial results (split-K style) -------------------------------------------------------------------
-        if (nt > 0) {
-            mbar_wait(&o_full[w], (nt - 1) & 1);
-            tc_fence_after();
-        }
-        // reference maxima: first 512 bytes of each warpgroup's own P buffer (free once its last P V has retired); the scaled rows go
-        // to the K/V ring, which is drained once ALL warpgroups are past their last o_full (first barrier)
-        float* mex = reinterpret_cast<float*>(smem + T3_OFF_P);
-        constexpr int MEX_LD = T3_P_BYTES / 4;
-        float* mbuf = reinterpret_cast<float*>(smem + T3_OFF_K);                   // [3][128][T3_MERGE_LD]
-        mex[w * MEX_LD + r] = m_ref;
-        asm volatile("bar.sync 1, 384;" ::: "memory");
-        const float M = fmaxf(mex[r], fmaxf(mex[MEX_LD + r], mex[2 * MEX_LD + r]));   // warpgroup 0 always has a tile: M is finite
-        const float f = nt > 0 ? ex2((m_ref - M) * scale_log2) : 0.f;
-        {
-            float* dst = mbuf + (w * 128 + r) * T3_MERGE_LD;
-            if (nt > 0) {
-                uint32_t tt[32];
-                tmem_ld_32x32(tO, tt);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(tt[i]) * f;
-                tmem_ld_32x32(tO + 32, tt);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) dst[32 + i] = __uint_as_float(tt[i]) * f;
-                tmem_ld_32x16(tO + 64, tt);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 9; ++i) dst[64 + i] = __uint_as_float(tt[i]) * f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 73; ++i) dst[i] = 0.f;
-            }
-        }
-        asm volatile("bar.sync 1, 384;" ::: "memory");
-        {   // thread (w, r) finishes head dims [24 w, 24 w + 24) of row r
-            const float* s0 = mbuf + r * T3_MERGE_LD;
-            const float* s1 = s0 + 128 * T3_MERGE_LD;
-            const float* s2 = s1 + 128 * T3_MERGE_LD;
-            const float inv = 1.0f / (s0[Dh] + s1[Dh] + s2[Dh]);
-            const int row = q0 + r;
-            if (row < Nq) {
-                __half* orow = out + (static_cast<size_t>(b) * Nq + row) * (H * Dh) + h * Dh;
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    const int d = 24 * w + 8 * g;
-                    if (d < Dh) {
-                        Pack8 v;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v.h[i] = __float2half_rn((s0[d + i] + s1[d + i] + s2[d + i]) * inv);
-                        *reinterpret_cast<uint4*>(orow + d) = v.u;
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        __syncwarp();
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-
 }  // namespace
 
 int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __half* out, int B, int H, int Nq, int Nk, int NkPad, int Dh, float scale,
@@ -1612,31 +861,12 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         TPX_CUDA(cudaFuncSetAttribute(attention_tc_p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-        TPX_CUDA(cudaFuncSetAttribute(attention_tc_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
-        TPX_CUDA(cudaFuncSetAttribute(attention_tc_3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
         attr_set = true;
     }
     ProfScope prof(PROF_ATTENTION, st);
     static const unsigned stagger = getenv("TPX_ATT_STAGGER") ? static_cast<unsigned>(atoi(getenv("TPX_ATT_STAGGER"))) : 1600u;   // cycles; see the de-phasing note in the kernel
     static const int stale_max = getenv("TPX_ATT_STALE_MAX") ? atoi(getenv("TPX_ATT_STALE_MAX")) : 1;   // 0: always reduce the maximum first
     dim3 grid((Nq + 2 * TA_BQ - 1) / (2 * TA_BQ), H, B);
-    if (variant == 3) {
-        CUtensorMap mKa3, mKb3;
-        if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 64, 64, &mKa3)) != TPX_OK) return rc;
-        if ((rc = make_tensor_map_2d(k, krows, TA_DHP, TA_DHP, 64, 16, &mKb3)) != TPX_OK) return rc;
-        dim3 grid3((Nq + TA_BQ - 1) / TA_BQ, H, B);
-        TPX_CUDA(launch_pdl(attention_tc_3_kernel, grid3, dim3(T3_THREADS), T3_SMEM, st, mQa, mQb, mKa3, mKb3, mV, out, H, Nq, Nk, Dh,
-                            scale * 1.4426950408889634f, dbg, stale_max ? 1 : 0));
-        TPX_LAUNCH_CHECK();
-        return TPX_OK;
-    }
-    static const int token = getenv("TPX_ATT_TOKEN") ? atoi(getenv("TPX_ATT_TOKEN")) : 0;   // variant 2: alternate the exponential phases
-    if (variant == 2) {
-        TPX_CUDA(launch_pdl(attention_tc_t_kernel, grid, dim3(TA_THREADS), TT_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh,
-                            scale * 1.4426950408889634f, dbg, stagger, (stale_max ? 1 : 0) | (token ? 2 : 0)));
-        TPX_LAUNCH_CHECK();
-        return TPX_OK;
-    }
     auto kern = variant == 0 ? (poly == 0 ? attention_tc_kernel<0> : attention_tc_kernel<4>) : (poly == 0 ? attention_tc_p_kernel<0> : attention_tc_p_kernel<4>);
     TPX_CUDA(launch_pdl(kern, grid, dim3(TA_THREADS), TA_SMEM, st, mQa, mQb, mKa, mKb, mV, out, H, Nq, Nk, Dh, scale * 1.4426950408889634f, dbg, stagger,
                         stale_max ? 1 : 0));

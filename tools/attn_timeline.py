@@ -14,14 +14,13 @@ for it in range(3):
     torch.cuda.synchronize()
 d = dbg.cpu().reshape(3, 1024)
 t0 = min(int(d[s, 2]) for s in range(3) if d[s, 0] > 0)
-V3 = os.environ.get("TPX_ATT_VARIANT") == "3"
-for s, name in enumerate(("WG_0", "WG_1", "WG_2") if V3 else ("WG_A", "WG_B", "MMA")):
+for s, name in enumerate(("WG_A", "WG_B", "MMA")):
     n = int(d[s, 0])
     ev = [(int(d[s, 1 + 2 * i]), int(d[s, 2 + 2 * i]) - t0) for i in range(n)]
     print(name, n, "events")
     print(" ".join(f"{tag}@{t}" for tag, t in ev[:120]))
 # per-phase mean durations over the steady-state iterations (fast path: tags 1 wait S, 2 S ready, 3 row loaded, 5 P buffer free, 6 exp+store done, 7 arrived)
-for s, name in (((0, "WG_0"), (1, "WG_1"), (2, "WG_2")) if V3 else ((0, "WG_A"), (1, "WG_B"))):
+for s, name in ((0, "WG_A"), (1, "WG_B")):
     n = int(d[s, 0])
     ev = [(int(d[s, 1 + 2 * i]), int(d[s, 2 + 2 * i]) - t0) for i in range(n)]
     iters, cur = [], {}
