@@ -157,11 +157,9 @@ static int map_conv(const void* ptr, long long P, int S, int C, int bk, CUtensor
     return TPX_OK;
 }
 
-int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes,
-                       CUtensorMap* out);
 // General fp16 tensor map (rank <= 5, dims / strides innermost first, strides in bytes for dims 1..rank-1); not cached.
 int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes,
-                       CUtensorMap* out) {
+                       CUtensorMap* out, int l2_promotion_bytes) {
     EncodeTiledFn enc = encode_fn();
     TPX_CHECK(enc != nullptr, TPX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
     TPX_CHECK(rank >= 1 && rank <= 5 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, TPX_ERR_ARG, "tensor map: rank %d / unaligned base", rank);
@@ -182,7 +180,11 @@ int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const l
                                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                         : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     l2_promotion_bytes >= 256  ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                     : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                     : l2_promotion_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                 : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TPX_CHECK(r == CUDA_SUCCESS, TPX_ERR_CUDA, "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, static_cast<int>(r));
     return TPX_OK;
 }
@@ -226,7 +228,7 @@ static int make_output_maps(const GemmProblem& p, GemmArgs& a, const CUtensorMap
             const long long C = p.N, dims[5] = {C, 4, 4, 4, p.M / 64};
             const long long strides[4] = {2 * C * 2, 16 * C * 2, 128 * C * 2, 512 * C * 2};
             const int box[5] = {64, 4, 4, 2, 1};
-            rc = make_tensor_map_nd(a.out0, 5, dims, strides, box, 128, &tc);
+            rc = make_tensor_map_nd(a.out0, 5, dims, strides, box, 128, &tc, 256);
         } else {
             TPX_CHECK(a.out0 != nullptr && a.ldo >= p.N, TPX_ERR_ARG, "gemm: output pointer / row stride (%d < N %d)", a.ldo, p.N);
             rc = map_2d(a.out0, p.M, p.N, a.ldo, 32, 64, &tc, 2);

@@ -43,7 +43,8 @@ int launch_attention_tc(const __half* q, const __half* k, const __half* vT, __ha
 // gemm_tc.cu : cached 2-D TMA descriptor over a row-major fp16 matrix (swizzle = box_cols * 2 bytes: 128/64/32)
 int make_tensor_map_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols, CUtensorMap* out);
 
-int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes, CUtensorMap* out);
+int make_tensor_map_nd(const void* ptr, int rank, const long long* dims, const long long* strides_bytes, const int* box, int swizzle_bytes, CUtensorMap* out,
+                       int l2_promotion_bytes = 256);
 void set_gemm_timeline(long long* dev_buf);
 
 // conv_halo.cu : 3x3x3 / pad 1 convolution on [P,8,8,8,C] volumes with the input block (+halo) staged ONCE per output tile

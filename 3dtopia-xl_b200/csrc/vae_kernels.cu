@@ -1,6 +1,8 @@
 // VAE-decoder kernels that are not GEMM shaped: the 1->C input convolution, GroupNorm(+SiLU) on
 // channels-last fp16 volumes, and the weight repacks into the implicit-GEMM [Cout, 27*Cin] layout.
 //   reference: models/vae3d_dib.py:93-145 (ResnetBlock), :344 (conv_in), :366-367 (norm_out / conv_out), :429
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace tpx {
@@ -171,12 +173,226 @@ __global__ void __launch_bounds__(256, RES > 0 ? 3 : 1) groupnorm_silu_kernel(co
     }
 }
 
+// Streaming version: persistent CTAs pull (primitive, channel slice) units of 32 or 64 KB through a 3-stage shared-memory ring with
+// TMA (two units in flight per CTA), compute the group statistics and the normalisation on the staged copy — ONE pass over HBM
+// whatever the volume size — and write the result with coalesced 16-byte stores.  A slice holds whole groups, so slices are
+// independent: the 8^3 x 256-channel tensor (262 KB per primitive, 537 MB in all) no longer needs a second read.  Statistics:
+// per-thread partials -> xor-shuffles across the lanes that own the same channel octet -> one 64-byte record per (warp, octet) ->
+// the first `oct` threads finish the sums in a fixed order (run-to-run bit-identical) and turn them into per-channel scale / shift
+// (groups of 1, 2, 4 or 8 channels never straddle an octet; no division, no global load in that serial section).
+// NT = 256: two CTAs per SM for the 32 KB units, so one CTA's exponentials run under the other's reduction; NT = 512: one CTA per SM
+// for the 64 KB units.  (1 024 threads per CTA measured 2x slower: three block-wide barriers per unit with 32 warps waiting.)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
+groupnorm_stream_kernel(const __grid_constant__ CUtensorMap tmIn, __half* __restrict__ out, const __half* __restrict__ gamma,
+                        const __half* __restrict__ beta, int S3, int C, int CW, int cpg, float eps, int apply_silu, int nunits, int NS, int box_rows) {
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(1024) uint8_t gsm_raw[];
+    uint8_t* gsm = gsm_raw + ((128u - (smem_u32(gsm_raw) & 127u)) & 127u);      // no swizzle: 128-byte alignment is enough
+    __shared__ __align__(16) float s_ss[32 * 16];            // [octet][8 scales, 8 shifts]
+    __shared__ float s_gamma[GN_MAXC], s_beta[GN_MAXC];
+    __shared__ __align__(8) uint64_t full[8];
+    for (int c = threadIdx.x; c < C; c += NT) {
+        s_gamma[c] = __half2float(gamma[c]);
+        s_beta[c] = __half2float(beta[c]);
+    }
+    const int unit_bytes = S3 * CW * 2;
+    float* s_red = reinterpret_cast<float*>(gsm + static_cast<size_t>(NS) * unit_bytes);   // [warp pair][octet][8 sums, 8 sums of squares]
+    const int slices = C / CW;
+    const int oct = CW >> 3;                   // 16-byte octets per voxel row of the slice (power of two, <= 32)
+    const int total = S3 * oct;
+    const int oct_shift = 31 - __clz(oct);
+    const float inv_n = 1.0f / static_cast<float>(S3 * cpg);
+    const int n_my = (nunits - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_oct = lane & (oct - 1);       // NT and 32 are multiples of oct: a thread always sees the same 8 channels
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmIn);
+        for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    auto load_unit = [&](int i) {
+        const int u = blockIdx.x + i * gridDim.x;
+        const int pp = u / slices, sl = u - pp * slices, st = i % NS;
+        uint8_t* dst = gsm + static_cast<size_t>(st) * unit_bytes;
+        mbar_arrive_expect_tx(&full[st], unit_bytes);
+        for (int r0 = 0; r0 < S3; r0 += box_rows) tma_load_2d(dst + static_cast<size_t>(r0) * CW * 2, &tmIn, &full[st], sl * CW, pp * S3 + r0);
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NS && i < n_my; ++i) load_unit(i);
+    for (int i = 0; i < n_my; ++i) {
+        const int st = i % NS;
+        const int u = blockIdx.x + i * gridDim.x;
+        const int pp = u / slices, sl = u - pp * slices;
+        mbar_wait(&full[st], (i / NS) & 1);
+        uint4* up = reinterpret_cast<uint4*>(gsm + static_cast<size_t>(st) * unit_bytes);
+        float ls[8], lq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ls[k] = 0.f; lq[k] = 0.f; }
+#pragma unroll 4
+        for (int j = threadIdx.x; j < total; j += NT) {
+            Pack8 v;
+            v.u = up[j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float f = __half2float(v.h[k]);
+                ls[k] += f;
+                lq[k] = fmaf(f, f, lq[k]);
+            }
+        }
+        for (int off = oct; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ls[k] += __shfl_xor_sync(0xffffffffu, ls[k], off);
+                lq[k] += __shfl_xor_sync(0xffffffffu, lq[k], off);
+            }
+        }
+        // upper half of the warps deposits its records, the lower half adds them to its own (halves the scratch: two CTAs per SM fit)
+        if (warp >= NW / 2 && lane < oct) {
+            float4* dst = reinterpret_cast<float4*>(s_red + ((warp - NW / 2) * oct + lane) * 16);
+            dst[0] = make_float4(ls[0], ls[1], ls[2], ls[3]);
+            dst[1] = make_float4(ls[4], ls[5], ls[6], ls[7]);
+            dst[2] = make_float4(lq[0], lq[1], lq[2], lq[3]);
+            dst[3] = make_float4(lq[4], lq[5], lq[6], lq[7]);
+        }
+        __syncthreads();
+        if (warp < NW / 2 && lane < oct) {
+            float4* dst = reinterpret_cast<float4*>(s_red + (warp * oct + lane) * 16);
+            const float4 a0 = dst[0], a1 = dst[1], b0 = dst[2], b1 = dst[3];
+            dst[0] = make_float4(ls[0] + a0.x, ls[1] + a0.y, ls[2] + a0.z, ls[3] + a0.w);
+            dst[1] = make_float4(ls[4] + a1.x, ls[5] + a1.y, ls[6] + a1.z, ls[7] + a1.w);
+            dst[2] = make_float4(lq[0] + b0.x, lq[1] + b0.y, lq[2] + b0.z, lq[3] + b0.w);
+            dst[3] = make_float4(lq[4] + b1.x, lq[5] + b1.y, lq[6] + b1.z, lq[7] + b1.w);
+        }
+        __syncthreads();
+        if (threadIdx.x < oct) {
+            float cs[8], cq[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { cs[k] = 0.f; cq[k] = 0.f; }
+#pragma unroll
+            for (int w = 0; w < NW / 2; ++w) {
+                const float4* src = reinterpret_cast<const float4*>(s_red + (w * oct + threadIdx.x) * 16);
+                const float4 a0 = src[0], a1 = src[1], b0 = src[2], b1 = src[3];
+                cs[0] += a0.x; cs[1] += a0.y; cs[2] += a0.z; cs[3] += a0.w; cs[4] += a1.x; cs[5] += a1.y; cs[6] += a1.z; cs[7] += a1.w;
+                cq[0] += b0.x; cq[1] += b0.y; cq[2] += b0.z; cq[3] += b0.w; cq[4] += b1.x; cq[5] += b1.y; cq[6] += b1.z; cq[7] += b1.w;
+            }
+            // group sums by butterfly (cpg in {1, 2, 4, 8}: groups never straddle the octet); every member ends up with its group's sums
+            if (cpg >= 2) {
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    const float a = cs[q] + cs[q + 1], b = cq[q] + cq[q + 1];
+                    cs[q] = cs[q + 1] = a;
+                    cq[q] = cq[q + 1] = b;
+                }
+            }
+            if (cpg >= 4) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if ((q & 2) == 0) {
+                        const float a = cs[q] + cs[q + 2], b = cq[q] + cq[q + 2];
+                        cs[q] = cs[q + 2] = a;
+                        cq[q] = cq[q + 2] = b;
+                    }
+            }
+            if (cpg >= 8) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float a = cs[q] + cs[q + 4], b = cq[q] + cq[q + 4];
+                    cs[q] = cs[q + 4] = a;
+                    cq[q] = cq[q + 4] = b;
+                }
+            }
+            const int c0 = sl * CW + threadIdx.x * 8;
+            float scv[8], shv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float mean = cs[q] * inv_n;
+                const float rstd = rsqrtf(fmaxf(cq[q] * inv_n - mean * mean, 0.f) + eps);
+                scv[q] = rstd * s_gamma[c0 + q];
+                shv[q] = s_beta[c0 + q] - mean * scv[q];
+            }
+            float4* dst = reinterpret_cast<float4*>(s_ss + threadIdx.x * 16);
+            dst[0] = make_float4(scv[0], scv[1], scv[2], scv[3]);
+            dst[1] = make_float4(scv[4], scv[5], scv[6], scv[7]);
+            dst[2] = make_float4(shv[0], shv[1], shv[2], shv[3]);
+            dst[3] = make_float4(shv[4], shv[5], shv[6], shv[7]);
+        }
+        __syncthreads();
+        float sc[8], sh[8];
+        {
+            const float4* src = reinterpret_cast<const float4*>(s_ss + my_oct * 16);
+            const float4 a0 = src[0], a1 = src[1], b0 = src[2], b1 = src[3];
+            sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+            sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+        }
+        // results leave through plain 16-byte stores (consecutive threads, consecutive octets of a row: coalesced), so the stage is
+        // free for the next TMA load as soon as every thread has read it: NS - 1 units stay in flight per CTA
+        uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(pp) * S3 * C + static_cast<size_t>(sl) * CW));
+        const int row_oct = C >> 3;
+#pragma unroll 4
+        for (int j = threadIdx.x; j < total; j += NT) {
+            Pack8 v, o;
+            v.u = up[j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float f = fmaf(__half2float(v.h[k]), sc[k], sh[k]);
+                if (apply_silu) f = silu_fast(f);
+                o.h[k] = __float2half_rn(f);
+            }
+            const int row = j >> oct_shift;
+            op[static_cast<size_t>(row) * row_oct + (j & (oct - 1))] = o.u;
+        }
+        __syncthreads();                       // every thread is done with this stage
+        if (threadIdx.x == 0 && i + NS < n_my) load_unit(i + NS);
+    }
+}
+
 int launch_groupnorm_silu(const __half* x, const __half* gamma, const __half* beta, int P, int S3, int C, int groups, float eps, int apply_silu,
                           __half* out, cudaStream_t st) {
     TPX_CHECK(C % 8 == 0 && C <= GN_MAXC && 256 % (C / 8) == 0 && groups > 0 && C % groups == 0, TPX_ERR_SHAPE,
               "groupnorm: channels %d / groups %d unsupported (C%%8==0, C<=%d, C/8 | 256)", C, groups, GN_MAXC);
     if (P <= 0) return TPX_OK;
     ProfScope prof(PROF_GROUPNORM, st);
+    // streaming path: units of 32 KB (whole primitive) or 64 KB (64-channel slice of a larger primitive)
+    static const bool stream_on = !(getenv("TPX_GN_STREAM") != nullptr && getenv("TPX_GN_STREAM")[0] == '0');
+    const int cpg = C / groups;
+    int CW = 0;
+    if (static_cast<long long>(S3) * C * 2 == 32768) CW = C;
+    else if (C % 64 == 0 && static_cast<long long>(S3) * 128 == 65536) CW = 64;
+    const bool cpg_ok = cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8;
+    if (stream_on && CW > 0 && cpg_ok && (CW & (CW - 1)) == 0 && CW >= 8 && (S3 <= 256 || S3 % 256 == 0)) {
+        const int unit_bytes = S3 * CW * 2;
+        const bool big = unit_bytes > 32768;
+        const int NT = big ? 512 : 256;
+        const int NS = 3;
+        const int box_rows = S3 < 256 ? S3 : 256;
+        const long long dims[2] = {C, static_cast<long long>(P) * S3};
+        const long long strides[1] = {2LL * C};
+        const int box[2] = {CW, box_rows};
+        CUtensorMap tmi;
+        // no L2 promotion beyond the row segment a unit really reads (a 256-byte promotion would fetch the neighbouring slices too)
+        int rc = make_tensor_map_nd(x, 2, dims, strides, box, 0, &tmi, CW * 2);
+        if (rc != TPX_OK) return rc;
+        const int nunits = P * (C / CW);
+        const int smem = NS * unit_bytes + (NT / 64) * (CW / 8) * 64 + 128;
+        static bool attr_set = false;
+        if (!attr_set) {
+            TPX_CUDA(cudaFuncSetAttribute(groupnorm_stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32768 + 8192 + 128));
+            TPX_CUDA(cudaFuncSetAttribute(groupnorm_stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 8192 + 128));
+            attr_set = true;
+        }
+        if (big) {
+            const int grid = nunits < 148 ? nunits : 148;
+            groupnorm_stream_kernel<512><<<grid, 512, smem, st>>>(tmi, out, gamma, beta, S3, C, CW, cpg, eps, apply_silu, nunits, NS, box_rows);
+        } else {
+            const int grid = nunits < 296 ? nunits : 296;      // two CTAs per SM: one's exponentials run under the other's reduction
+            groupnorm_stream_kernel<256><<<grid, 256, smem, st>>>(tmi, out, gamma, beta, S3, C, CW, cpg, eps, apply_silu, nunits, NS, box_rows);
+        }
+        TPX_LAUNCH_CHECK();
+        return TPX_OK;
+    }
     if (S3 * (C / 8) == 8 * 256) groupnorm_silu_kernel<8><<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
     else groupnorm_silu_kernel<0><<<P, 256, 0, st>>>(x, gamma, beta, S3, C, groups, eps, apply_silu, out);
     TPX_LAUNCH_CHECK();
