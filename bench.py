@@ -429,8 +429,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": "configs[1]: image-cond DDIM-25 step, CFG 6, 2048 tokens x 1370 ctx tokens, fp16, 1 sample per GPU (2 sequences per forward)",
-                   "samples_per_gpu": BS, "respacing": respacing, "cfg_scale": CFG_SCALE, "parallelism": f"dp{world} (one sample per GPU, no collective in the step loop)",
+        "config": {"workload": f"configs[1]: image-cond DDIM-25 step, CFG 6, 2048 tokens x 1370 ctx tokens, fp16, {BS} sample{'s' if BS > 1 else ''} per GPU ({2 * BS} sequences per forward)",
+                   "samples_per_gpu": BS, "respacing": respacing, "cfg_scale": CFG_SCALE, "parallelism": f"dp{world} ({BS} sample{'s' if BS > 1 else ''} per GPU, no collective in the step loop)",
                    "l2": "each step streams 1.8 GB of fp16 weights (> 126 MB L2), so no separate L2 flush is needed"},
         "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

@@ -24,6 +24,6 @@ timeout 250 ncu --set full --clock-control none --import-source on -k regex:atte
     python bench.py --steps 1 --warmup 3 --no-vae --no-cpu > $O/${TAG}_ncu_a.log 2>&1; echo "attention capture rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 300 -c 6 -f -o $O/${TAG}_prof_gemm \
     python bench.py --steps 1 --warmup 3 --no-vae --no-cpu > $O/${TAG}_ncu_g.log 2>&1; echo "gemm capture rc=$?"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"conv3_halo|groupnorm_silu" -s 9 -c 6 -f -o $O/${TAG}_prof_vae \
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"conv3_halo|groupnorm" -s 9 -c 6 -f -o $O/${TAG}_prof_vae \
     python tools/vae_decode_perf.py 1 > $O/${TAG}_ncu_v.log 2>&1; echo "vae capture rc=$?"
 python -c "import json; d=json.load(open('$O/${TAG}_bench.json')); print('steps/s', round(d['value'],1), 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value'],1), 'clocks', d['clocks'])"
