@@ -69,9 +69,11 @@ def test_sampler_step_matches_oracle(ddim, eta):
         assert (got["sample"] - ref["sample"]).abs().max() < tol * max(1.0, float(ref["sample"].abs().max()))
 
 
-@pytest.mark.parametrize("S3,Cc,silu", [(64, 256, 1), (512, 256, 1), (512, 32, 1), (64, 256, 0)])
-def test_groupnorm_silu(S3, Cc, silu):
-    P = 5
+# P = 5: one unit per CTA of the streaming kernel; the large P values make every persistent CTA walk its 3-stage TMA ring several
+# times (stage reuse, barrier parity flips); (96, 64) is a shape the streaming kernel does not take (per-primitive fallback kernel)
+@pytest.mark.parametrize("S3,Cc,silu,P", [(64, 256, 1, 5), (512, 256, 1, 5), (512, 32, 1, 5), (64, 256, 0, 5), (64, 256, 1, 1500), (512, 32, 0, 1500),
+                                          (512, 256, 1, 300), (96, 64, 1, 7)])
+def test_groupnorm_silu(S3, Cc, silu, P):
     x = (torch.randn(P, S3, Cc, device="cuda") * 2 + 0.3).half()
     gamma, beta = (torch.randn(Cc, device="cuda") * 0.1 + 1).half(), (torch.randn(Cc, device="cuda") * 0.1).half()
     out = torch.empty_like(x)
