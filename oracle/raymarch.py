@@ -1,10 +1,13 @@
 """Oracle restatement of the MVP ray-march preview (TEST INFRASTRUCTURE — see oracle/__init__.py).
 
-PARITY UNPINNED against the reference's CUDA extension: `dva/mvp/extensions/mvpraymarch` is an sm_70 torch extension that needs a
-GPU and its own build, neither available where the fixtures are made, so this file is a reading of the sources, not checked
-against their outputs.  What pins it instead: the reference's OWN pure-PyTorch ray-marcher (the comparison arm of its gradcheck
-script, mvpraymarch.py:391-475) is restated here as `raymarch_dense`, and tests/test_oracle_golden.py holds the kernel-shaped
-restatement `raymarch` to it on scenes where the two must agree.
+PINNED to the reference's own pure-PyTorch ray-marcher, not to its CUDA extension: `dva/mvp/extensions/mvpraymarch` is an sm_70 torch
+extension that needs a GPU and its own build, neither available where the fixtures are made.  The reference's gradcheck script carries
+a plain PyTorch implementation of the same forward pass as the arm its CUDA kernel is checked against (mvpraymarch.py:391-475);
+tests/golden/make_raymarch_golden.py EXECUTES that block from /root/reference on the CPU over a seeded scene and stores inputs + image
+in tests/golden/raymarch_ref.npz.  tests/test_oracle_golden.py holds `raymarch_dense` (the restatement of that block) to the fixture
+at 2.4e-7 and the kernel-shaped restatement `raymarch` at 1.3e-6, and additionally `raymarch` to `raymarch_dense` on a camera scene.
+What stays a reading of the sources without reference output behind it: the CUDA-only parts — the per-warp hit list with its 512-entry
+cap, the start-at-first-hit stepping and compute_raydirs' slab test.
 
 Restates (file:line under /root/reference):
   * convert_camera_parameters            dva/ray_marcher.py:24-33

@@ -242,3 +242,24 @@ def test_raymarch_restatement_agrees_with_the_reference_torch_marcher():
     assert float(b[..., 3].max()) > 0.3
     rel = float((a - b).norm() / b.norm())
     assert rel < 2e-2, rel
+
+
+def test_raymarch_oracle_matches_the_reference_torch_marcher_fixture(golden_dir):
+    """tests/golden/raymarch_ref.npz holds the image the REFERENCE's own pure-PyTorch ray-marcher (the block its gradcheck script runs
+    against the CUDA kernel, mvpraymarch.py:391-475) produced for a seeded scene; tests/golden/make_raymarch_golden.py executed that
+    block from /root/reference on the CPU.  Both oracle restatements are held to it: `raymarch_dense` (the same algorithm) tightly,
+    `raymarch` (the CUDA kernel's structure, which the GPU test compares the kernel with) up to float rounding on this scene, whose
+    rays carry their own [tmin, tmax] so the two formulations take the same steps."""
+    import torch
+    from oracle import raymarch as rmo
+    d = np.load(os.path.join(golden_dir, "raymarch_ref.npz"))
+    t = lambda k: torch.from_numpy(d[k])[0]      # noqa: E731  (one batch element)
+    args = (t("raypos"), t("raydir"), float(d["stepsize"]), t("tminmax"), t("template_chlast"), t("primpos"), t("primrot"), t("primscale"),
+            float(d["fadescale"]), float(d["fadeexp"]))
+    ref = t("rayrgba")
+    assert float((ref[..., 3] > 0).float().mean()) > 0.5 and float((ref[..., 3] >= 1 - 1e-6).float().mean()) > 0.1   # covered and saturating rays
+    dense = rmo.raymarch_dense(*args)
+    assert float((dense - ref).abs().max()) < 5e-6, float((dense - ref).abs().max())
+    kern = rmo.raymarch(*args)
+    assert float((kern - ref).abs().max()) < 2e-5, float((kern - ref).abs().max())
+
