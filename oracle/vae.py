@@ -109,3 +109,32 @@ def pack_decoded(decoded: Tensor, bs: int, num_prims: int) -> Tensor:
     d[:, 0:1] /= 5.0
     d[:, 1:] = (d[:, 1:] + 1) / 2.0
     return d.reshape(bs, num_prims, -1)
+
+
+def inference_glue(sample: Tensor, decode, latent_mean: Tensor, latent_std: Tensor, latent_nf: float, perchannel_norm: bool) -> Tensor:
+    """inference.py:328-348, statement by statement (variable names kept), with `decode` standing in for vae.decode:
+    latent de-normalisation, 0:4 | 4:68 slicing, per-sample decode, inverse feature normalisation (sdf / 5, (rgb, mat + 1) / 2 — and, without
+    per-channel statistics, srt scale / 10 + 0.05 and the decoder input / latent_nf), channel-major packing, concat -> [bs, prims, 4 + 6*512].
+    Pinned bit for bit to the reference's own statements executed by tests/golden/make_inference_glue_golden.py (inference_glue.npz)."""
+    inf_bs, num_prims = sample.shape[0], sample.shape[1]
+    latent = torch.empty(1, num_prims, 1, 4, 4, 4)
+    recon_param = sample.reshape(inf_bs, num_prims, -1)
+    if perchannel_norm:
+        recon_param = recon_param / latent_nf * latent_std + latent_mean
+    recon_srt_param = recon_param[:, :, 0:4]
+    recon_feat_param = recon_param[:, :, 4:]
+    recon_feat_param_list = []
+    for inf_bidx in range(inf_bs):
+        if not perchannel_norm:
+            decoded = decode(recon_feat_param[inf_bidx, ...].reshape(1 * num_prims, *latent.shape[-4:]) / latent_nf)
+        else:
+            decoded = decode(recon_feat_param[inf_bidx, ...].reshape(1 * num_prims, *latent.shape[-4:]))
+        recon_feat_param_list.append(decoded.detach())
+    recon_feat_param = torch.concat(recon_feat_param_list, dim=0)
+    if not perchannel_norm:
+        recon_srt_param[:, :, 0:1] = (recon_srt_param[:, :, 0:1] / 10) + 0.05
+    recon_feat_param[:, 0:1, ...] /= 5.
+    recon_feat_param[:, 1:, ...] = (recon_feat_param[:, 1:, ...] + 1) / 2.
+    recon_feat_param = recon_feat_param.reshape(inf_bs, num_prims, -1)
+    return torch.concat([recon_srt_param, recon_feat_param], dim=-1)
+

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import oracle
 import tpxl_b200
 from tpxl_b200 import synth
 from gpu_util import rel_l2
@@ -15,29 +16,9 @@ DEV = torch.device("cuda:0")
 P = 2048
 
 
-def _reference_glue(sample, decode, latent_mean, latent_std, latent_nf, perchannel_norm):
-    """inference.py:328-348 verbatim (variable names kept), with `decode` standing in for vae.decode."""
-    inf_bs, num_prims = sample.shape[0], sample.shape[1]
-    latent = torch.empty(1, num_prims, 1, 4, 4, 4)
-    recon_param = sample.reshape(inf_bs, num_prims, -1)
-    if perchannel_norm:
-        recon_param = recon_param / latent_nf * latent_std + latent_mean
-    recon_srt_param = recon_param[:, :, 0:4]
-    recon_feat_param = recon_param[:, :, 4:]
-    recon_feat_param_list = []
-    for inf_bidx in range(inf_bs):
-        if not perchannel_norm:
-            decoded = decode(recon_feat_param[inf_bidx, ...].reshape(1 * num_prims, *latent.shape[-4:]) / latent_nf)
-        else:
-            decoded = decode(recon_feat_param[inf_bidx, ...].reshape(1 * num_prims, *latent.shape[-4:]))
-        recon_feat_param_list.append(decoded.detach())
-    recon_feat_param = torch.concat(recon_feat_param_list, dim=0)
-    if not perchannel_norm:
-        recon_srt_param[:, :, 0:1] = (recon_srt_param[:, :, 0:1] / 10) + 0.05
-    recon_feat_param[:, 0:1, ...] /= 5.
-    recon_feat_param[:, 1:, ...] = (recon_feat_param[:, 1:, ...] + 1) / 2.
-    recon_feat_param = recon_feat_param.reshape(inf_bs, num_prims, -1)
-    return torch.concat([recon_srt_param, recon_feat_param], dim=-1)
+# inference.py:328-348 restated once, in the oracle, where tests/test_oracle_golden.py pins it bit for bit to the reference's own statements
+# (tests/golden/inference_glue.npz, produced by executing that block of /root/reference/inference.py)
+_reference_glue = oracle.vae.inference_glue
 
 
 @pytest.mark.parametrize("perchannel,nf", [(True, 1.0), (True, 0.7), (False, 1.0), (False, 1.3)])

@@ -263,3 +263,30 @@ def test_raymarch_oracle_matches_the_reference_torch_marcher_fixture(golden_dir)
     kern = rmo.raymarch(*args)
     assert float((kern - ref).abs().max()) < 2e-5, float((kern - ref).abs().max())
 
+
+def test_inference_glue_matches_the_reference_statements(golden_dir):
+    """tests/golden/inference_glue.npz: `recon_param` as the REFERENCE's own statements (inference.py:328-348, executed from
+    /root/reference by tests/golden/make_inference_glue_golden.py with an index-revealing stand-in for vae.decode) produce it, for both
+    settings of perchannel_norm and two latent_nf.  The oracle restatement — which the CUDA glue kernels are held to on the GPU — must
+    reproduce it bit for bit (same eager fp32 ops on the CPU)."""
+    import torch
+    d = np.load(os.path.join(golden_dir, "inference_glue.npz"))
+
+    def fake_decode(z):
+        n = z.shape[0]
+        base = torch.arange(n * 6 * 512, dtype=torch.float32).reshape(n, 6, 8, 8, 8)
+        return base * 1e-3 - 3.0 + z.reshape(n, -1).sum(1).reshape(n, 1, 1, 1, 1)
+
+    sample, mean, std = (torch.from_numpy(d[k]) for k in ("sample", "latent_mean", "latent_std"))
+    prims = sample.shape[1] // 68
+    n = 0
+    for key in d.files:
+        if not key.startswith("recon_param_"):
+            continue
+        pc = key.split("_pc")[1][0] == "1"
+        nf = float(key.split("_nf")[1])
+        got = oracle.vae.inference_glue(sample.clone().reshape(sample.shape[0], prims, 68), fake_decode, mean, std, nf, pc)
+        assert torch.equal(got, torch.from_numpy(d[key])), key
+        n += 1
+    assert n == 4
+
