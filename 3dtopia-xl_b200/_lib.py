@@ -48,6 +48,9 @@ SIGNATURES = {
     "tpx_dit_workspace_bytes": (_sz, [_vp, _i]),
     "tpx_dit_set_cond": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "tpx_dit_forward": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _sz, _vp]),
+    "tpx_dit_timesteps_bytes": (_sz, [_vp, _i]),
+    "tpx_dit_set_timesteps": (_i, [_vp, C.POINTER(_i64), _i, _vp, _sz, _vp]),
+    "tpx_dit_forward_step": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "tpx_dit_debug_residual": (_i, [_vp, _vp, _i, _vp, _vp]),
     "tpx_sampler_step": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, C.POINTER(SamplerCoefs), _vp, _vp, _vp]),
     "tpx_latent_split": (_i, [_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp]),

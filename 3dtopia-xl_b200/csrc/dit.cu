@@ -32,6 +32,9 @@ struct tpx_dit {
     __half *ck = nullptr, *cv = nullptr, *y16 = nullptr;
     int cond_n = 0, cond_M = 0, cond_MP = 0;
     bool tc_attn = false;                 // tcgen05 attention (Dh == 72, N % 8 == 0); V kept transposed
+    // timestep table (tpx_dit_set_timesteps): modulation rows [K, Ltot] of a sampling schedule's timesteps, in caller memory
+    __half* ts_table = nullptr;
+    std::vector<long long> ts_values;
 };
 
 static size_t al8(size_t n) { return (n + 7) & ~static_cast<size_t>(7); }
@@ -181,6 +184,30 @@ DitWs carve_ws(const tpx_dit* h, int S, uint8_t* base) {
     return w;
 }
 
+// Timestep table: [K, Ltot] fp16 modulation rows | K int64 timesteps (device copy) | scratch of one chunk of TS_CHUNK timesteps
+constexpr int TS_CHUNK = 8;    // = the batched GEMV's maximum batch: the adaLN weights are streamed once per 8 timesteps
+constexpr int TS_MAX = 4096;
+struct TsWs {
+    __half* table;
+    long long* t_dev;
+    float *th1, *temb;
+    __half* ts16;
+    size_t total;
+};
+
+TsWs carve_ts(const tpx_dit* h, int K, uint8_t* base) {
+    TsWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = base == nullptr ? nullptr : base + off; off += (bytes + 255) & ~static_cast<size_t>(255); return p; };
+    w.table = reinterpret_cast<__half*>(take(static_cast<size_t>(K) * h->Ltot * 2));
+    w.t_dev = reinterpret_cast<long long*>(take(static_cast<size_t>(K) * 8));
+    w.th1 = reinterpret_cast<float*>(take(static_cast<size_t>(TS_CHUNK) * h->D * 4));
+    w.temb = reinterpret_cast<float*>(take(static_cast<size_t>(TS_CHUNK) * h->D * 4));
+    w.ts16 = reinterpret_cast<__half*>(take(static_cast<size_t>(TS_CHUNK) * h->D * 2));
+    w.total = off;
+    return w;
+}
+
 // tile width for the 2-CTA kernel (256-row pair tiles over gemm_num_sms()/2 clusters)
 int pick_bn_2cta(int M, int N) {
     const int pairs = gemm_num_sms() / 2;
@@ -301,6 +328,8 @@ int tpx_dit_set_weight(tpx_dit* h, const char* ref_key, const void* dev_ptr, int
         if (h->required[i] == key) h->seen[i] = 1;
     if (key == "null_cond_embedding") h->has_null = true;
     h->finalized = false;
+    h->ts_values.clear();       // a timestep table derived from the previous weights is stale
+    h->ts_table = nullptr;
     return TPX_OK;
 }
 
@@ -379,9 +408,11 @@ int tpx_dit_set_cond(tpx_dit* h, const float* y, int n_cross, int M, void* cond_
     return TPX_OK;
 }
 
-int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use_cfg, float cfg_scale, void* out, void* ws, size_t ws_bytes,
-                    void* stream) {
-    TPX_CHECK(h != nullptr && x != nullptr && t != nullptr && out != nullptr && ws != nullptr, TPX_ERR_ARG, "dit_forward: null argument");
+// One forward.  The modulation vectors of the step come either from `t` (device timesteps: timestep MLP + the adaLN GEMV pass run here and
+// fill the workspace's [B, Ltot] table) or, when `t` is null, from `mod_rows` = one precomputed row shared by the whole batch (tpx_dit_forward_step).
+static int dit_forward_impl(tpx_dit* h, const float* x, const int64_t* t, const __half* mod_rows, int B, int use_cfg, float cfg_scale, void* out, void* ws,
+                            size_t ws_bytes, void* stream) {
+    TPX_CHECK(h != nullptr && x != nullptr && (t != nullptr || mod_rows != nullptr) && out != nullptr && ws != nullptr, TPX_ERR_ARG, "dit_forward: null argument");
     TPX_CHECK(h->finalized, TPX_ERR_STATE, "dit_forward: weights not finalized");
     TPX_CHECK(B >= 1 && B <= 8, TPX_ERR_SHAPE, "dit_forward: batch %d must be in [1,8]", B);
     TPX_CHECK(use_cfg >= 0 && use_cfg <= 2, TPX_ERR_ARG, "dit_forward: use_cfg %d", use_cfg);
@@ -415,10 +446,18 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     // The head-split GEMM epilogues write only the Dh real columns of each 80-wide head row (24-column bulk stores); the padding
     // columns / rows of q, k, v(T) must be zero, so the three buffers (contiguous in the workspace) are cleared once per forward.
     TPX_CUDA(cudaMemsetAsync(w.q, 0, reinterpret_cast<uint8_t*>(w.ao) - reinterpret_cast<uint8_t*>(w.q), st));
-    // timestep embedding (fp32) -> silu -> fp16, then every adaLN modulation of the network in one GEMV pass
-    TPX_RC(launch_gemv(GEMV_IN_TIMESTEP, GEMV_OUT_F32_SILU, h->Wt0, h->bt0, nullptr, reinterpret_cast<const long long*>(t), B, D, 256, w.th1, nullptr, D, st));
-    TPX_RC(launch_gemv(GEMV_IN_F32, GEMV_OUT_F32_AND_SILU16, h->Wt2, h->bt2, w.th1, nullptr, B, D, D, w.temb, w.ts16, D, st));
-    TPX_RC(launch_gemv(GEMV_IN_F16, GEMV_OUT_F16, h->Wada, h->bada, w.ts16, nullptr, B, Ltot, D, w.mod, nullptr, Ltot, st));
+    // timestep embedding (fp32) -> silu -> fp16, then every adaLN modulation of the network in one GEMV pass — unless the row of this
+    // step was hoisted out of the sampling loop (tpx_dit_set_timesteps): then the whole batch reads that one row (batch stride 0)
+    const __half* mod_base = w.mod;
+    int mod_bs = Ltot;
+    if (t != nullptr) {
+        TPX_RC(launch_gemv(GEMV_IN_TIMESTEP, GEMV_OUT_F32_SILU, h->Wt0, h->bt0, nullptr, reinterpret_cast<const long long*>(t), B, D, 256, w.th1, nullptr, D, st));
+        TPX_RC(launch_gemv(GEMV_IN_F32, GEMV_OUT_F32_AND_SILU16, h->Wt2, h->bt2, w.th1, nullptr, B, D, D, w.temb, w.ts16, D, st));
+        TPX_RC(launch_gemv(GEMV_IN_F16, GEMV_OUT_F16, h->Wada, h->bada, w.ts16, nullptr, B, Ltot, D, w.mod, nullptr, Ltot, st));
+    } else {
+        mod_base = mod_rows;
+        mod_bs = 0;
+    }
     // token embedding, fp32, written to both CFG halves
     TPX_RC(launch_x_embed(x, h->Wx, h->bx, B * N, h->Cin, D, w.xres, use_cfg ? static_cast<long long>(B) * N * D : 0, st));
 
@@ -426,9 +465,9 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     const size_t per_layer_v = h->tc_attn ? static_cast<size_t>(h->cond_n) * h->H * h->cond_MP * h->DhP : per_layer_kv;
     for (int i = 0; i < h->L; ++i) {
         const DitLayer& l = h->layers[i];
-        const __half* mod = w.mod + static_cast<size_t>(i) * 9 * D;   // (shift,scale,gate) x (mca,msa,mlp)
+        const __half* mod = mod_base + static_cast<size_t>(i) * 9 * D;   // (shift,scale,gate) x (mca,msa,mlp)
         // ---- cross-attention branch (sequences [0,Sc)) ----
-        TPX_RC(launch_ln_modulate(w.xres, Sc * N, D, 1e-6f, mod + 0 * D, mod + 1 * D, Ltot, N, B, w.h16, nullptr, nullptr, 0, st));
+        TPX_RC(launch_ln_modulate(w.xres, Sc * N, D, 1e-6f, mod + 0 * D, mod + 1 * D, mod_bs, N, B, w.h16, nullptr, nullptr, 0, st));
         {
             GemmArgs a{};
             a.bias = l.bq; a.post_scale = qscale; a.out0 = w.q;
@@ -440,11 +479,11 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         {
             GemmArgs a{};
             a.bias = l.bcp; a.post_scale = 1.0f; a.xres = w.xres; a.ldx = D;
-            a.gate = mod + 2 * D; a.gate_bstride = Ltot; a.rows_per_batch = N; a.gate_batches = B;
+            a.gate = mod + 2 * D; a.gate_bstride = mod_bs; a.rows_per_batch = N; a.gate_batches = B;
             TPX_RC(gemm_linear(w.ao, D, l.Wcp, Sc * N, D, D, EPI_GATED, a, 0, st));
         }
         // ---- self-attention branch (all sequences); the collapsed cross-attention of the null half is added here ----
-        TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, mod + 3 * D, mod + 4 * D, Ltot, N, B, w.h16, Sc < S ? mod + 2 * D : nullptr,
+        TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, mod + 3 * D, mod + 4 * D, mod_bs, N, B, w.h16, Sc < S ? mod + 2 * D : nullptr,
                                   h->uconst + static_cast<size_t>(i) * D, Sc * N, st));
         {
             GemmArgs a{};
@@ -458,11 +497,11 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         {
             GemmArgs a{};
             a.bias = l.bsp; a.post_scale = 1.0f; a.xres = w.xres; a.ldx = D;
-            a.gate = mod + 5 * D; a.gate_bstride = Ltot; a.rows_per_batch = N; a.gate_batches = B;
+            a.gate = mod + 5 * D; a.gate_bstride = mod_bs; a.rows_per_batch = N; a.gate_batches = B;
             TPX_RC(gemm_linear(w.ao, D, l.Wsp, S * N, D, D, EPI_GATED, a, 0, st));
         }
         // ---- MLP branch ----
-        TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, mod + 6 * D, mod + 7 * D, Ltot, N, B, w.h16, nullptr, nullptr, 0, st));
+        TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, mod + 6 * D, mod + 7 * D, mod_bs, N, B, w.h16, nullptr, nullptr, 0, st));
         {
             GemmArgs a{};
             a.bias = l.b1; a.post_scale = 1.0f; a.out0 = w.hid; a.ldo = h->Dm;
@@ -471,13 +510,13 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
         {
             GemmArgs a{};
             a.bias = l.b2; a.post_scale = 1.0f; a.xres = w.xres; a.ldx = D;
-            a.gate = mod + 8 * D; a.gate_bstride = Ltot; a.rows_per_batch = N; a.gate_batches = B;
+            a.gate = mod + 8 * D; a.gate_bstride = mod_bs; a.rows_per_batch = N; a.gate_batches = B;
             TPX_RC(gemm_linear(w.hid, h->Dm, l.W2, S * N, D, h->Dm, EPI_GATED, a, 0, st));
         }
     }
     // ---- final layer ----
-    const __half* fmod = w.mod + static_cast<size_t>(h->L) * 9 * D;
-    TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, fmod, fmod + D, Ltot, N, B, w.h16, nullptr, nullptr, 0, st));
+    const __half* fmod = mod_base + static_cast<size_t>(h->L) * 9 * D;
+    TPX_RC(launch_ln_modulate(w.xres, S * N, D, 1e-6f, fmod, fmod + D, mod_bs, N, B, w.h16, nullptr, nullptr, 0, st));
     {
         GemmArgs a{};
         a.bias = h->bfl; a.post_scale = 1.0f; a.out0 = use_cfg ? w.fin : static_cast<__half*>(out); a.ldo = h->Cout;
@@ -486,6 +525,57 @@ int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use
     if (use_cfg) TPX_RC(launch_cfg_combine(w.fin, static_cast<long long>(B) * N * h->Cout, cfg_scale, static_cast<__half*>(out), st));
 #undef TPX_RC
     return TPX_OK;
+}
+
+int tpx_dit_forward(tpx_dit* h, const float* x, const int64_t* t, int B, int use_cfg, float cfg_scale, void* out, void* ws, size_t ws_bytes,
+                    void* stream) {
+    TPX_CHECK(t != nullptr, TPX_ERR_ARG, "dit_forward: null timesteps");
+    return dit_forward_impl(h, x, t, nullptr, B, use_cfg, cfg_scale, out, ws, ws_bytes, stream);
+}
+
+size_t tpx_dit_timesteps_bytes(const tpx_dit* h, int K) {
+    if (h == nullptr || K <= 0 || K > TS_MAX) return 0;
+    return carve_ts(h, K, nullptr).total;
+}
+
+int tpx_dit_set_timesteps(tpx_dit* h, const int64_t* t_host, int K, void* ts_ws, size_t ts_bytes, void* stream) {
+    TPX_CHECK(h != nullptr && t_host != nullptr && ts_ws != nullptr, TPX_ERR_ARG, "dit_set_timesteps: null argument");
+    TPX_CHECK(h->finalized, TPX_ERR_STATE, "dit_set_timesteps: weights not finalized (load_state_dict first)");
+    TPX_CHECK(K >= 1 && K <= TS_MAX, TPX_ERR_SHAPE, "dit_set_timesteps: %d timesteps (1..%d)", K, TS_MAX);
+    TPX_CHECK(ts_bytes >= tpx_dit_timesteps_bytes(h, K), TPX_ERR_ARG, "dit_set_timesteps: table store too small (%zu < %zu)", ts_bytes,
+              tpx_dit_timesteps_bytes(h, K));
+    TPX_CHECK((reinterpret_cast<uintptr_t>(ts_ws) & 255) == 0, TPX_ERR_ARG, "dit_set_timesteps: store must be 256-B aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const TsWs w = carve_ts(h, K, static_cast<uint8_t*>(ts_ws));
+    h->ts_values.clear();
+    h->ts_table = nullptr;
+    // pageable source: the driver stages the values before the call returns, so t_host need not outlive it
+    TPX_CUDA(cudaMemcpyAsync(w.t_dev, t_host, static_cast<size_t>(K) * 8, cudaMemcpyHostToDevice, st));
+    const int D = h->D, Ltot = h->Ltot;
+    for (int c = 0; c < K; c += TS_CHUNK) {
+        const int nb = K - c < TS_CHUNK ? K - c : TS_CHUNK;
+        // the same three launches a forward issues for its batch (utils.py:27-64, dit_crossattn.py:54,75), over 8 timesteps at once:
+        // per output element the arithmetic does not depend on the batch it runs in, so a row equals what tpx_dit_forward computes
+        int rc = launch_gemv(GEMV_IN_TIMESTEP, GEMV_OUT_F32_SILU, h->Wt0, h->bt0, nullptr, w.t_dev + c, nb, D, 256, w.th1, nullptr, D, st);
+        if (rc != TPX_OK) return rc;
+        rc = launch_gemv(GEMV_IN_F32, GEMV_OUT_F32_AND_SILU16, h->Wt2, h->bt2, w.th1, nullptr, nb, D, D, w.temb, w.ts16, D, st);
+        if (rc != TPX_OK) return rc;
+        rc = launch_gemv(GEMV_IN_F16, GEMV_OUT_F16, h->Wada, h->bada, w.ts16, nullptr, nb, Ltot, D, w.table + static_cast<size_t>(c) * Ltot, nullptr, Ltot, st);
+        if (rc != TPX_OK) return rc;
+    }
+    h->ts_values.assign(t_host, t_host + K);
+    h->ts_table = w.table;
+    return TPX_OK;
+}
+
+int tpx_dit_forward_step(tpx_dit* h, const float* x, int64_t t, int B, int use_cfg, float cfg_scale, void* out, void* ws, size_t ws_bytes, void* stream) {
+    TPX_CHECK(h != nullptr, TPX_ERR_ARG, "dit_forward_step: null handle");
+    TPX_CHECK(h->ts_table != nullptr && !h->ts_values.empty(), TPX_ERR_STATE, "dit_forward_step: no timestep table (call tpx_dit_set_timesteps after loading weights)");
+    size_t row = h->ts_values.size();
+    for (size_t i = 0; i < h->ts_values.size(); ++i)
+        if (h->ts_values[i] == static_cast<long long>(t)) { row = i; break; }
+    TPX_CHECK(row < h->ts_values.size(), TPX_ERR_STATE, "dit_forward_step: timestep %lld is not in the table given to tpx_dit_set_timesteps", (long long)t);
+    return dit_forward_impl(h, x, nullptr, h->ts_table + row * static_cast<size_t>(h->Ltot), B, use_cfg, cfg_scale, out, ws, ws_bytes, stream);
 }
 
 int tpx_dit_debug_residual(const tpx_dit* h, const void* ws, int n_seq, float* out, void* stream) {

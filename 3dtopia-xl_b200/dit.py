@@ -11,14 +11,17 @@ What is different underneath (results stay within the fp16 tolerance of the refe
   * cross-attention K/V of all blocks are computed once per conditioning tensor ``y`` and cached
     (the cache holds a strong reference to that tensor and compares identity + version counter), not once per step;
   * under ``forward_with_cfg`` the null-conditioned half of the batch does not run cross-attention at
-    all: with an all-equal context the softmax is uniform and the branch equals a per-block constant.
+    all: with an all-equal context the softmax is uniform and the branch equals a per-block constant;
+  * the timestep embedding and all 29 adaLN modulation Linears depend only on ``t``: ``set_timesteps`` computes them once for a
+    sampling schedule's timesteps (8 per pass over the 669 MB of adaLN weights) and a forward that is told its timestep on the
+    host (``t_host=``, what ``SpacedDiffusion``'s loops do) reads the row instead of re-running them — bit-identical results.
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
 from collections import OrderedDict
-from typing import Dict, Iterator, Optional
+from typing import Dict, Iterator, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -54,6 +57,8 @@ class DiT(nn.Module):
         self._cond_key = None
         self._resident_only = False                     # True once the host copy was released (release_state_dict / load_checkpoint)
         self._cond_ref: Optional[torch.Tensor] = None   # strong reference to the cached y: its address cannot be recycled while cached
+        self._ts_ws: Optional[torch.Tensor] = None      # timestep table (set_timesteps): modulation rows of a schedule's timesteps
+        self._ts_key: Optional[tuple] = None
         self.collapse_null_branch = True     # set False to run the null half through real cross-attention (tests)
 
     # ---- parameters: reference key names, values kept as given (CPU or GPU, fp16 or fp32) ----------------
@@ -156,6 +161,7 @@ class DiT(nn.Module):
         self._handle, self._handle_device = h, dev
         self._ws.clear()
         self._cond_ws, self._cond_key, self._cond_ref = None, None, None
+        self._ts_ws, self._ts_key = None, None
         self._ingest()
 
     def _ingest(self):
@@ -178,6 +184,7 @@ class DiT(nn.Module):
             _lib.check(lib.tpx_dit_finalize(self._handle, st), "tpx_dit_finalize")
             torch.cuda.current_stream().synchronize()
         self._cond_key, self._cond_ref = None, None
+        self._ts_key = None                        # the C library dropped its timestep table with the first set_weight
         if released:                               # re-ingested after a device move of a released model: release again
             self._sd = None
 
@@ -230,7 +237,30 @@ class DiT(nn.Module):
         _lib.check(lib.tpx_dit_set_cond(self._handle, yy.data_ptr(), n_cross, M, self._aligned(self._cond_ws), nbytes, _lib.stream_ptr()), "tpx_dit_set_cond")
         self._cond_key, self._cond_ref = key, y
 
-    def _run(self, x, t, y, use_cfg: int, cfg_scale: float, enable_amp: bool):
+    def set_timesteps(self, timesteps: Sequence[int], force: bool = False) -> None:
+        """Hoist TimestepEmbedder + every adaLN_modulation Linear (models/utils.py:27-64, dit_crossattn.py:40-43,54,66-69,75) out of a
+        sampling loop: compute the modulation vectors of all of a schedule's ORIGINAL-schedule timesteps (``SpacedDiffusion.timestep_map``)
+        once.  A later ``forward(..., t_host=t)`` / ``forward_with_cfg(..., t_host=t)`` with ``t`` among them reads its row; any other call
+        computes them per step as before.  Recomputed only when the list changes (or ``force``); reloading weights drops the table."""
+        self._require_handle()
+        ts = tuple(int(v) for v in timesteps)
+        if not ts:
+            raise ValueError("set_timesteps: empty timestep list")
+        if not force and ts == self._ts_key:
+            return
+        lib = _lib.lib()
+        with torch.cuda.device(self._handle_device):
+            nbytes = lib.tpx_dit_timesteps_bytes(self._handle, len(ts))
+            if nbytes == 0:
+                raise _lib.TpxError(f"set_timesteps: {len(ts)} timesteps is outside what the table holds (1..4096)")
+            if self._ts_ws is None or self._ts_ws.numel() < nbytes + 256:
+                self._ts_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._handle_device)
+            self._ts_key = None
+            arr = (C.c_int64 * len(ts))(*ts)
+            _lib.check(lib.tpx_dit_set_timesteps(self._handle, arr, len(ts), self._aligned(self._ts_ws), nbytes, _lib.stream_ptr()), "tpx_dit_set_timesteps")
+        self._ts_key = ts
+
+    def _run(self, x, t, y, use_cfg: int, cfg_scale: float, enable_amp: bool, t_host: Optional[int] = None):
         self._require_handle()
         if x.dim() != 3 or x.shape[1] != self.seq_length or x.shape[2] != self.in_channels:
             raise ValueError(f"x must be [B,{self.seq_length},{self.in_channels}], got {tuple(x.shape)}")
@@ -253,19 +283,26 @@ class DiT(nn.Module):
             ws = self._workspace(n_seq)
             out = torch.empty(B, self.seq_length, self.out_channels, dtype=torch.float16, device=dev)
             nbytes = lib.tpx_dit_workspace_bytes(self._handle, n_seq)
-            _lib.check(lib.tpx_dit_forward(self._handle, xx.data_ptr(), tt.data_ptr(), B, use_cfg, float(cfg_scale), out.data_ptr(), self._aligned(ws),
-                                           nbytes, _lib.stream_ptr()), "tpx_dit_forward")
+            if t_host is not None and self._ts_key is not None and int(t_host) in self._ts_key:
+                # the caller states (on the host) that every sample of the batch sits at timestep t_host and its modulation row is in the
+                # table: no timestep MLP, no adaLN pass, and the device tensor t is not read
+                _lib.check(lib.tpx_dit_forward_step(self._handle, xx.data_ptr(), int(t_host), B, use_cfg, float(cfg_scale), out.data_ptr(),
+                                                    self._aligned(ws), nbytes, _lib.stream_ptr()), "tpx_dit_forward_step")
+            else:
+                _lib.check(lib.tpx_dit_forward(self._handle, xx.data_ptr(), tt.data_ptr(), B, use_cfg, float(cfg_scale), out.data_ptr(), self._aligned(ws),
+                                               nbytes, _lib.stream_ptr()), "tpx_dit_forward")
         # the reference returns fp16 under autocast and fp32 otherwise (dit_crossattn.py:197-202)
         return out if enable_amp else out.float()
 
-    def forward(self, x, t, y, precision_dtype=torch.float32, enable_amp=False):
-        """DiT.forward (dit_crossattn.py:184-202).
+    def forward(self, x, t, y, precision_dtype=torch.float32, enable_amp=False, t_host: Optional[int] = None):
+        """DiT.forward (dit_crossattn.py:184-202).  ``t_host`` (not a reference argument, optional): the caller's promise that every
+        entry of ``t`` equals this Python int — lets the call use the table of ``set_timesteps`` (see there); results do not change.
 
         PRECISION: the kernels implement ONE contract, the reference's CUDA autocast(fp16) path (what inference.py / app.py run:
         ``precision: fp16`` + ``amp``).  ``enable_amp=False`` or ``precision_dtype != float16`` does NOT select an fp32 (or bf16)
         computation here: the same fp16-contract result is returned, cast to fp32 when amp is off, and a warning says so once."""
         self._precision_notice(precision_dtype, enable_amp)
-        return self._run(x, t, y, 0, 0.0, enable_amp)
+        return self._run(x, t, y, 0, 0.0, enable_amp, t_host)
 
     _warned_precision = False
 
@@ -277,10 +314,10 @@ class DiT(nn.Module):
                           f"(got precision_dtype={precision_dtype}, enable_amp={enable_amp}); the output is fp16-accurate, returned as "
                           f"{'fp16' if enable_amp else 'fp32'}", stacklevel=3)
 
-    def forward_with_cfg(self, x, t, y, cfg_scale=0.0, precision_dtype=torch.float32, enable_amp=False):
-        """DiT.forward_with_cfg (dit_crossattn.py:204-213).  Precision: see forward()."""
+    def forward_with_cfg(self, x, t, y, cfg_scale=0.0, precision_dtype=torch.float32, enable_amp=False, t_host: Optional[int] = None):
+        """DiT.forward_with_cfg (dit_crossattn.py:204-213).  Precision and ``t_host``: see forward()."""
         self._precision_notice(precision_dtype, enable_amp)
-        return self._run(x, t, y, 1 if self.collapse_null_branch else 2, cfg_scale, enable_amp)
+        return self._run(x, t, y, 1 if self.collapse_null_branch else 2, cfg_scale, enable_amp, t_host)
 
     def debug_residual(self, n_seq: int) -> torch.Tensor:
         """fp32 residual stream [n_seq, N, D] left by the last forward (parity tests)."""

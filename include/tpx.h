@@ -88,6 +88,19 @@ int tpx_dit_set_cond(tpx_dit* h, const float* y_dev, int n_cross, int M, void* c
  *                exists so tests can check the constant identity on the device. */
 int tpx_dit_forward(tpx_dit* h, const float* x_dev, const int64_t* t_dev, int B, int use_cfg, float cfg_scale, void* out_f16_dev, void* ws,
                     size_t ws_bytes, void* stream);
+/* Hoist of TimestepEmbedder (models/utils.py:27-64) and of every adaLN_modulation Linear (dit_crossattn.py:40-43,54 and :66-69,75)
+ * out of the sampling loop: they depend only on the timestep, and a sampling loop visits a fixed list of them
+ * (SpacedDiffusion.timestep_map, respace.py:73-87; gaussian_diffusion.py:674-685 feeds the same t to the whole batch).
+ * tpx_dit_set_timesteps computes the [K, 28*9*D + 2*D] fp16 modulation rows of K original-schedule timesteps (host int64 array)
+ * into caller memory `ts_ws` (256-B aligned, tpx_dit_timesteps_bytes(h, K) bytes, must stay alive and untouched while used) with
+ * the same kernels and the same per-element arithmetic a forward uses, 8 timesteps per pass over the 669 MB of adaLN weights.
+ * tpx_dit_forward_step is tpx_dit_forward for a batch whose B samples all sit at timestep `t`: it reads the row of `t` from that
+ * table instead of running the timestep MLP and the adaLN pass (results are bit-identical to tpx_dit_forward).  `t` must be one
+ * of the K values (TPX_ERR_STATE otherwise); loading a weight invalidates the table. */
+size_t tpx_dit_timesteps_bytes(const tpx_dit* h, int K);
+int tpx_dit_set_timesteps(tpx_dit* h, const int64_t* t_host, int K, void* ts_ws, size_t ts_bytes, void* stream);
+int tpx_dit_forward_step(tpx_dit* h, const float* x_dev, int64_t t, int B, int use_cfg, float cfg_scale, void* out_f16_dev, void* ws, size_t ws_bytes,
+                         void* stream);
 /* Debug / parity: copy the fp32 residual stream [n_seq, N, hidden] left in `ws` by the last forward. */
 int tpx_dit_debug_residual(const tpx_dit* h, const void* ws, int n_seq, float* out_dev, void* stream);
 

@@ -147,3 +147,66 @@ def test_full_size_ddim_properties():
     assert all(torch.isfinite(s).all() for s in steps)
     assert torch.equal(again, steps[0])
     assert rel_l2(solo, steps[0][1:2]) < 1e-3
+
+
+# ---- timestep table (DiT.set_timesteps / tpx_dit_forward_step): the hoisted timestep MLP + adaLN rows must change nothing -----------------
+def test_timestep_table_rows_are_bit_identical_to_the_per_step_computation():
+    sd, m, x, y = _setup(57)
+    d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
+    tmap = list(d.timestep_map)                    # 25 timesteps -> 4 table passes (8 + 8 + 8 + 1): first / middle / lone-last rows below
+    with torch.no_grad():
+        plain = {t: m.forward_with_cfg(x, torch.tensor([t, t], device=DEV), y, cfg_scale=6.0, enable_amp=True).clone() for t in (0, 280, 320, 600, 960)}
+        plain_fwd = m.forward(x, torch.tensor([600, 600], device=DEV), y, torch.float16, True).clone()
+        m.set_timesteps(tmap)
+        for t, ref in plain.items():
+            got = m.forward_with_cfg(x, torch.tensor([t, t], device=DEV), y, cfg_scale=6.0, enable_amp=True, t_host=t)
+            assert torch.equal(got, ref), t
+        assert torch.equal(m.forward(x, torch.tensor([600, 600], device=DEV), y, torch.float16, True, t_host=600), plain_fwd)
+        # one sample per batch (B = 1) reads the same row
+        one = m.forward_with_cfg(x[:1], torch.tensor([320], device=DEV), y[:1].contiguous(), cfg_scale=6.0, enable_amp=True).clone()
+        assert torch.equal(m.forward_with_cfg(x[:1], torch.tensor([320], device=DEV), y[:1].contiguous(), cfg_scale=6.0, enable_amp=True, t_host=320), one)
+        # a timestep that is not in the table: the call computes it per step as before
+        off = m.forward_with_cfg(x, torch.tensor([333, 333], device=DEV), y, cfg_scale=6.0, enable_amp=True).clone()
+        assert torch.equal(m.forward_with_cfg(x, torch.tensor([333, 333], device=DEV), y, cfg_scale=6.0, enable_amp=True, t_host=333), off)
+        assert not torch.equal(off, plain[320])
+
+
+def test_timestep_table_is_dropped_when_weights_change():
+    sd, m, x, y = _setup(59)
+    t = torch.tensor([480, 480], device=DEV)
+    with torch.no_grad():
+        m.set_timesteps([480, 520])
+        a = m.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True, t_host=480).clone()
+        sd2 = synth.synth_state_dict(synth.dit_shapes(**CFG), 60)
+        m.load_state_dict(sd2)                       # re-ingests: a table derived from the old adaLN weights must not be used
+        assert m._ts_key is None
+        b = m.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True, t_host=480).clone()
+        fresh = tpxl_b200.DiT(**CFG)
+        fresh.load_state_dict(sd2)
+        fresh = fresh.to(DEV).eval()
+        c = fresh.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True)
+        m.set_timesteps([480, 520])
+        e = m.forward_with_cfg(x, t, y, cfg_scale=6.0, enable_amp=True, t_host=480)
+    assert not torch.equal(a, b) and torch.equal(b, c) and torch.equal(e, c)
+    with pytest.raises(tpxl_b200._lib.TpxError):     # straight at the C ABI: a timestep outside the table is an error there, not a fallback
+        lib = tpxl_b200._lib.lib()
+        ws = m._workspace(4)
+        out = torch.empty(2, 256, 136, dtype=torch.float16, device=DEV)
+        tpxl_b200._lib.check(lib.tpx_dit_forward_step(m._handle, x.data_ptr(), 7, 2, 1, 6.0, out.data_ptr(), m._aligned(ws),
+                                                      lib.tpx_dit_workspace_bytes(m._handle, 4), tpxl_b200._lib.stream_ptr()))
+
+
+@pytest.mark.parametrize("ddim", [True, False])
+def test_sampling_loop_is_unchanged_by_the_timestep_hoist(ddim):
+    sd, m, x, y = _setup(61)
+    kw = dict(y=y, cfg_scale=6.0, precision_dtype=torch.float16, enable_amp=True)
+    runs = []
+    for hoist in (False, True):
+        d = tpxl_b200.create_diffusion("ddim25" if ddim else "10", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+        d.hoist_timesteps = hoist
+        m._ts_key = None
+        fn = d.ddim_sample_loop_progressive if ddim else d.p_sample_loop_progressive
+        torch.manual_seed(5)
+        runs.append([o["sample"].clone() for o in fn(m.forward_with_cfg, x.shape, x, clip_denoised=False, model_kwargs=kw, progress=False, device=DEV)])
+        assert (m._ts_key is not None) == hoist
+    assert len(runs[0]) == len(runs[1]) and all(torch.equal(a, b) for a, b in zip(*runs))
