@@ -151,6 +151,20 @@ class SpacedDiffusion:
                                             x_prev.data_ptr(), x0.data_ptr(), _lib.stream_ptr()), "tpx_sampler_step")
         return {"sample": x_prev, "pred_xstart": x0}
 
+    def _hoist_owner(self, model: Callable, model_kwargs: dict):
+        """The DiT whose timestep table this loop may build and address (``t_host=``), or None.  Only this package's own, un-overridden
+        ``DiT.forward`` / ``DiT.forward_with_cfg`` qualify — as a bound method (inference.py:278-280 passes ``model.forward_with_cfg`` /
+        ``model.forward``) or as the module itself (``__call__`` -> ``forward``); any wrapper, subclass override or other model is called with
+        the reference's arguments only."""
+        from .dit import DiT
+        if not self.hoist_timesteps or "t_host" in model_kwargs:
+            return None
+        if isinstance(model, DiT):
+            owner, target = model, type(model).forward
+        else:
+            owner, target = getattr(model, "__self__", None), getattr(model, "__func__", None)
+        return owner if isinstance(owner, DiT) and target in (DiT.forward, DiT.forward_with_cfg) else None
+
     def _loop(self, ddim: bool, model: Callable, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress, eta) -> Iterator[Dict[str, torch.Tensor]]:
         if denoised_fn is not None or cond_fn is not None:
             raise NotImplementedError("denoised_fn / cond_fn are not on the released inference path and are not implemented")
@@ -169,12 +183,8 @@ class SpacedDiffusion:
         t_all = torch.tensor(self.timestep_map, dtype=torch.int64, device=device)
         # this package's DiT called through its bound forward / forward_with_cfg: the loop knows every timestep on the host, so the
         # timestep embedding + adaLN rows of the whole schedule are computed once here and each step names its row (t_host)
-        from .dit import DiT
-        if isinstance(model, DiT):                 # the module itself: __call__ -> forward
-            owner, target = model, type(model).forward
-        else:                                      # a bound method (inference.py:278-280 passes model.forward_with_cfg / model.forward)
-            owner, target = getattr(model, "__self__", None), getattr(model, "__func__", None)
-        hoist = self.hoist_timesteps and isinstance(owner, DiT) and target in (DiT.forward, DiT.forward_with_cfg) and "t_host" not in model_kwargs
+        owner = self._hoist_owner(model, model_kwargs)
+        hoist = owner is not None
         if hoist:
             owner.set_timesteps(self.timestep_map)
         if progress:

@@ -191,3 +191,31 @@ def test_respacing_strings_match_reference(golden_dir):
                 space_timesteps(1000, spec)
         else:
             assert sorted(space_timesteps(1000, spec)) == want, spec
+
+
+def test_timestep_hoist_is_offered_only_to_this_packages_own_dit_methods():
+    """SpacedDiffusion's loops may build DiT's timestep table and pass ``t_host=`` only when the model they are handed is the package's
+    un-overridden DiT.forward / forward_with_cfg (bound method or module); everything else must see the reference's call signature."""
+    import tpxl_b200
+    d = tpxl_b200.create_diffusion("ddim25", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    cfg = dict(seq_length=8, in_channels=8, condition_channels=16, hidden_size=128, depth=1, num_heads=8)
+    m = tpxl_b200.DiT(**cfg)
+    assert d.hoist_timesteps
+    assert d._hoist_owner(m.forward_with_cfg, {}) is m and d._hoist_owner(m.forward, {"y": None}) is m and d._hoist_owner(m, {}) is m
+    assert d._hoist_owner(lambda x, t, **kw: m.forward_with_cfg(x, t, **kw), {}) is None          # a wrapper (e.g. respace._WrappedModel)
+    assert d._hoist_owner(torch.nn.Linear(2, 2), {}) is None and d._hoist_owner(torch.nn.Linear(2, 2).forward, {}) is None
+    assert d._hoist_owner(m.forward_with_cfg, {"t_host": 3}) is None                                 # the caller already decides
+
+    class Sub(tpxl_b200.DiT):
+        def forward_with_cfg(self, x, t, y, **kw):      # an override need not know t_host
+            return super().forward_with_cfg(x, t, y, **kw)
+
+    s = Sub(**cfg)
+    assert d._hoist_owner(s.forward_with_cfg, {}) is None and d._hoist_owner(s.forward, {}) is s and d._hoist_owner(s, {}) is s
+    d.hoist_timesteps = False
+    assert d._hoist_owner(m.forward_with_cfg, {}) is None
+    # the two reference signatures still bind positionally (inference.py:278-280 passes keywords; gaussian_diffusion.py:279 positionals + kwargs)
+    import inspect
+    for fn in (tpxl_b200.DiT.forward, tpxl_b200.DiT.forward_with_cfg):
+        names = list(inspect.signature(fn).parameters)
+        assert names[:4] == ["self", "x", "t", "y"] and names[-1] == "t_host" and inspect.signature(fn).parameters["t_host"].default is None
