@@ -49,7 +49,9 @@ def test_sass_contains_blackwell_tensor_and_tma_ops(lib):
     import subprocess
     obj = os.path.join(ROOT, "3dtopia-xl_b200", "build", "gemm_tc.o")
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
-    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+    # tensor-core MMA (1-CTA and cta_group::2), TMA loads, TMEM loads, and the bulk-store epilogues: plain tensor stores and the
+    # L2-side reduce-add that carries the gated residual (no `UTMASTG` in round 1: per-thread 16-byte stores)
+    for mnem in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "LDTM", "UTMASTG", "UTMAREDG"):
         assert mnem in sass, mnem
 
 
