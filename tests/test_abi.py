@@ -66,6 +66,14 @@ def test_compute_path_fails_loudly_without_gpu():
     with pytest.raises(_lib.TpxError):
         list(tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v").ddim_sample_loop_progressive(
             lambda *a, **k: None, (1, 8, 8), noise=torch.zeros(1, 8, 8), device="cpu"))
+    with pytest.raises(_lib.TpxError):
+        m.set_timesteps([0, 40])                     # the timestep table lives in the C library: no handle, no table
+    # argument validation of the timestep-table entries happens before any CUDA call
+    raw = _lib.load_library()
+    assert raw.tpx_dit_timesteps_bytes(None, 25) == 0
+    arr = (ctypes.c_int64 * 2)(0, 40)
+    assert raw.tpx_dit_set_timesteps(None, arr, 2, None, 0, None) == -1 and b"null" in raw.tpx_last_error()
+    assert raw.tpx_dit_forward_step(None, None, 0, 1, 1, 6.0, None, None, 0, None) == -1
 
 
 def test_schedule_matches_reference_fixture(golden_dir):
