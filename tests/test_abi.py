@@ -118,6 +118,26 @@ def test_step_coefficients_are_fp32_rounded_like_extract_into_tensor():
             assert k.nonzero == (0.0 if i == 0 else 1.0)
 
 
+def test_host_coefficients_and_update_order_reproduce_the_reference_with_clip(golden_dir):
+    """The DDIM update the CUDA kernel performs (ddim_step_kernel: one explicitly rounded fp32 op per reference tensor op, the clamp of
+    process_xstart in between) restated in numpy float32 on the HOST coefficients of SpacedDiffusion.step_coefs — product code that runs
+    without a GPU — reproduces the reference sampler's 25-step clip_denoised=True trajectory BIT FOR BIT (fixture: the reference's own
+    sampler on replayed model outputs, tests/golden/make_sampler_clip_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "sampler_clip.npz"))
+    d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
+    f = np.float32
+    x = g["x_T"].copy()
+    for n, i in enumerate(reversed(range(25))):
+        k = d.step_coefs(i, 0.0, True)
+        assert k.clip == 1 and float(k.sigma) == 0.0
+        v = g["outs25"][n][..., :68]
+        x0 = (f(k.sqrt_ab) * x - f(k.sqrt_1mab) * v).astype(f)
+        x0 = np.minimum(np.maximum(x0, f(-1)), f(1))
+        eps = ((f(k.sqrt_recip_ab) * x - x0) / f(k.sqrt_recipm1_ab)).astype(f)
+        x = (x0 * f(k.c_x0) + f(k.c_eps) * eps).astype(f)
+        assert np.array_equal(x0, g["ddim25_x0"][n]) and np.array_equal(x, g["ddim25_samples"][n]), n
+
+
 def test_state_dict_contract_on_host(golden_dir):
     keys = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
     m = tpxl_b200.DiT(**{k: v for k, v in synth.FULL_DIT.items()})

@@ -53,17 +53,21 @@ def test_cfg_combine_matches_fp16_arithmetic():
     assert torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("ddim,eta", [(True, 0.0), (True, 0.5), (False, 0.0)])
-def test_sampler_step_matches_oracle(ddim, eta):
+# clip: the clamp of process_xstart (gaussian_diffusion.py:310-315; clip_denoised=True is the reference's default argument): with these
+# inputs about a third of the predicted x_0 entries leave [-1, 1]
+@pytest.mark.parametrize("ddim,eta,clip", [(True, 0.0, False), (True, 0.5, False), (False, 0.0, False), (True, 0.0, True), (True, 0.5, True), (False, 0.0, True)])
+def test_sampler_step_matches_oracle(ddim, eta, clip):
     d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v")
     s = oracle.diffusion.Schedule("ddim25")
     x = torch.randn(2, 256, 68, device="cuda")
     mo = torch.randn(2, 256, 136, device="cuda").half()
     noise = torch.randn_like(x)
     for i in (24, 7, 0):
-        got = d._step(ddim, x, mo, i, eta, False, noise)
-        ref = oracle.diffusion.ddim_step(s, x, mo.float(), i, eta, noise) if ddim else oracle.diffusion.ddpm_step(s, x, mo.float(), i, noise)
+        got = d._step(ddim, x, mo, i, eta, clip, noise)
+        ref = oracle.diffusion.ddim_step(s, x, mo.float(), i, eta, noise, clip) if ddim else oracle.diffusion.ddpm_step(s, x, mo.float(), i, noise, clip)
         torch.cuda.synchronize()
+        if clip:
+            assert float(got["pred_xstart"].abs().max()) <= 1.0 and float((got["pred_xstart"].abs() == 1.0).float().mean()) > 0.05
         tol = 2e-6 if ddim else 2e-3     # DDPM: the reference's fp16 (var+1)/2 arithmetic vs the oracle's fp32
         assert (got["pred_xstart"] - ref["pred_xstart"]).abs().max() < 2e-6
         assert (got["sample"] - ref["sample"]).abs().max() < tol * max(1.0, float(ref["sample"].abs().max()))

@@ -210,3 +210,27 @@ def test_sampling_loop_is_unchanged_by_the_timestep_hoist(ddim):
         runs.append([o["sample"].clone() for o in fn(m.forward_with_cfg, x.shape, x, clip_denoised=False, model_kwargs=kw, progress=False, device=DEV)])
         assert (m._ts_key is not None) == hoist
     assert len(runs[0]) == len(runs[1]) and all(torch.equal(a, b) for a, b in zip(*runs))
+
+
+def test_clip_denoised_loop_reproduces_the_reference_fixture(golden_dir):
+    """clip_denoised=True (the reference's default argument) through the CUDA loop: seeded model outputs replayed through the REFERENCE
+    sampler on the CPU are the fixture (tests/golden/make_sampler_clip_golden.py); the same outputs replayed through this package's loop on
+    the GPU must give the same 25 samples / clamped x_0 predictions (same fp32 ops in the same order: a few ulp at most)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "sampler_clip.npz"))
+    x_T = torch.from_numpy(g["x_T"]).to(DEV)
+    outs = iter(torch.from_numpy(g["outs25"]).to(DEV))
+    d = tpxl_b200.create_diffusion("ddim25", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization="v")
+    seen_t = []
+
+    def replay(x, t, **kw):
+        seen_t.append(t.tolist())
+        return next(outs)
+
+    traj = list(d.ddim_sample_loop_progressive(replay, tuple(x_T.shape), x_T, clip_denoised=True, model_kwargs={}, progress=False, device=DEV))
+    assert len(traj) == 25 and seen_t[0] == [960, 960] and seen_t[-1] == [0, 0]
+    for i, o in enumerate(traj):
+        assert float(o["pred_xstart"].abs().max()) <= 1.0
+        assert rel_l2(o["pred_xstart"], torch.from_numpy(g["ddim25_x0"][i]).to(DEV)) < 1e-5, i
+        assert rel_l2(o["sample"], torch.from_numpy(g["ddim25_samples"][i]).to(DEV)) < 1e-5, i

@@ -124,6 +124,35 @@ def test_ddpm_trajectory_matches_reference(golden_dir):
         assert _rel(o["sample"], g["ddpm10_samples"][i]) < 5e-5, i
 
 
+def test_sampler_with_clip_denoised_matches_reference(golden_dir):
+    """clip_denoised=True is the default of every sampling entry point of the reference (gaussian_diffusion.py:399,442,487,536,656); the
+    fixture replays seeded model outputs through the REFERENCE sampler with the clamp of process_xstart (:310-315) active on ~30 % of
+    the entries (tests/golden/make_sampler_clip_golden.py).  With the model replayed, the oracle's arithmetic is the reference's op for op."""
+    g = _load(golden_dir, "sampler_clip.npz")
+    x_T = torch.from_numpy(g["x_T"])
+    assert 0.1 < float(g["clamped_fraction"]) < 0.6
+
+    def replay(outs):
+        it = iter(torch.from_numpy(outs))
+        return lambda xx, tt: next(it)
+
+    s25, s10 = oracle.diffusion.Schedule("ddim25"), oracle.diffusion.Schedule("10")
+    traj = list(oracle.diffusion.sample_loop(s25, replay(g["outs25"]), x_T, ddim=True, clip_denoised=True))
+    for i, o in enumerate(traj):
+        assert float(o["pred_xstart"].abs().max()) <= 1.0
+        assert _rel(o["pred_xstart"], g["ddim25_x0"][i]) < 1e-6 and _rel(o["sample"], g["ddim25_samples"][i]) < 1e-6, i
+    torch.manual_seed(11)
+    traj = list(oracle.diffusion.sample_loop(s25, replay(g["outs25"]), x_T, ddim=True, eta=0.5, clip_denoised=True, step_noise=torch.randn_like))
+    assert max(_rel(o["sample"], g["ddim25_eta05_samples"][i]) for i, o in enumerate(traj)) < 1e-6
+    torch.manual_seed(12)
+    traj = list(oracle.diffusion.sample_loop(s10, replay(g["outs10"]), x_T, ddim=False, clip_denoised=True, step_noise=torch.randn_like))
+    for i, o in enumerate(traj):
+        assert _rel(o["pred_xstart"], g["ddpm10_x0"][i]) < 1e-6 and _rel(o["sample"], g["ddpm10_samples"][i]) < 1e-6, i
+    # and the fixture does see the clamp: the unclamped oracle leaves it
+    plain = list(oracle.diffusion.sample_loop(s25, replay(g["outs25"]), x_T, ddim=True, clip_denoised=False))
+    assert _rel(plain[0]["pred_xstart"], g["ddim25_x0"][0]) > 1e-2
+
+
 def test_vae_decode_matches_reference(golden_dir):
     g = _load(golden_dir, "vae_decode.npz")
     sd = synth.synth_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 103)
