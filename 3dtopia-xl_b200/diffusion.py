@@ -9,9 +9,11 @@ Host work per step: one model call and ONE kernel launch for the whole update (t
 kernels and 12 pageable host->device copies per step).  Schedule tables are float64 numpy,
 evaluated per step and rounded to fp32 exactly like ``_extract_into_tensor`` (gaussian_diffusion.py:880-892).
 
-Scope: v-prediction with learned-range variance — the only configuration the released
-model uses (configs/inference_dit.yml:67-71).  Other parameterisations raise NotImplementedError, as the
-reference does for unknown ones (__init__.py:36).
+Scope: learned-range variance (``learn_sigma=True``) with any of the three parameterisations
+``create_diffusion`` knows (__init__.py:27-36): "v" — the released model (configs/inference_dit.yml:67-71) — "eps" (the
+reference's default argument) and "xstart".  They differ only in how x_0 is predicted from the model output
+(gaussian_diffusion.py:319-328), always of the form a·x_t − b·out, so the one update kernel serves all three with per-step (a, b)
+from the host tables.  Fixed variances (``learn_sigma=False``: the model returns C channels, not 2C) raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -73,12 +75,15 @@ def _f32(v: float) -> np.float32:
 
 
 class SpacedDiffusion:
-    """Respaced Gaussian diffusion, v-prediction + learned-range variance, CUDA update step."""
+    """Respaced Gaussian diffusion, learned-range variance, v / eps / xstart prediction, CUDA update step."""
 
     def __init__(self, use_timesteps, betas: np.ndarray, parameterization: str = "v", learn_sigma: bool = True):
-        if parameterization != "v" or not learn_sigma:
-            raise NotImplementedError("Model Mean Type {} / learn_sigma={} is not supported by the B200 sampler kernel "
-                                      "(released model: parameterization 'v', learn_sigma True)".format(parameterization, learn_sigma))
+        if parameterization not in ("v", "eps", "xstart"):
+            raise NotImplementedError("Model Mean Type {} is not supported!".format(parameterization))
+        if not learn_sigma:
+            raise NotImplementedError("learn_sigma=False (fixed variances, C-channel model output) is not supported by the B200 sampler kernel "
+                                      "(released model: learn_sigma True)")
+        self.parameterization = parameterization
         self.use_timesteps = set(use_timesteps)
         self.original_num_steps = len(betas)
         base_ac = np.cumprod(1.0 - np.asarray(betas, dtype=np.float64))
@@ -112,8 +117,18 @@ class SpacedDiffusion:
     # ---- per-step coefficients, rounded exactly like the reference's fp32 tensor arithmetic -------------------
     def step_coefs(self, i: int, eta: float = 0.0, clip_denoised: bool = False) -> _lib.SamplerCoefs:
         k = _lib.SamplerCoefs()
-        k.sqrt_ab = _f32(self.sqrt_alphas_cumprod[i])
-        k.sqrt_1mab = _f32(self.sqrt_one_minus_alphas_cumprod[i])
+        # pred_xstart = a * x_t - b * model_output, one rounding per op in the kernel exactly as the reference's tensor ops:
+        #   "v"      a = sqrt(ab),    b = sqrt(1-ab)       _predict_xstart_from_z_and_v   (gaussian_diffusion.py:340-344)
+        #   "eps"    a = sqrt(1/ab),  b = sqrt(1/ab-1)     _predict_xstart_from_eps       (:346-351)
+        #   "xstart" a = 0,           b = -1               the model output itself        (:319-320): 0*x - (-1*out) = out exactly
+        if self.parameterization == "v":
+            a, b = self.sqrt_alphas_cumprod[i], self.sqrt_one_minus_alphas_cumprod[i]
+        elif self.parameterization == "eps":
+            a, b = self.sqrt_recip_alphas_cumprod[i], self.sqrt_recipm1_alphas_cumprod[i]
+        else:
+            a, b = 0.0, -1.0
+        k.sqrt_ab = _f32(a)
+        k.sqrt_1mab = _f32(b)
         k.sqrt_recip_ab = _f32(self.sqrt_recip_alphas_cumprod[i])
         k.sqrt_recipm1_ab = _f32(self.sqrt_recipm1_alphas_cumprod[i])
         ab, abp, one = _f32(self.alphas_cumprod[i]), _f32(self.alphas_cumprod_prev[i]), np.float32(1.0)

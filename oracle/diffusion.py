@@ -90,23 +90,32 @@ def _f32(table: np.ndarray, i: int) -> torch.Tensor:
     return torch.tensor(float(table[i]), dtype=torch.float64).float()
 
 
-def predict(s: Schedule, x: torch.Tensor, model_out: torch.Tensor, i: int, clip_denoised: bool = False) -> Dict[str, torch.Tensor]:
-    """p_mean_variance for VELOCITY + LEARNED_RANGE (gaussian_diffusion.py:280-338)."""
+def predict(s: Schedule, x: torch.Tensor, model_out: torch.Tensor, i: int, clip_denoised: bool = False, parameterization: str = "v") -> Dict[str, torch.Tensor]:
+    """p_mean_variance with LEARNED_RANGE variance (gaussian_diffusion.py:280-338) for the three model-mean types create_diffusion maps
+    its ``parameterization`` argument to (__init__.py:27-34): "v" VELOCITY (:325-328, :340-344 — the released model), "eps" EPSILON
+    (:321-324, :346-351), "xstart" START_X (:319-320)."""
     C = x.shape[-1]
     v, var_values = torch.split(model_out, C, dim=-1)
     min_log, max_log = _f32(s.posterior_log_variance_clipped, i), _f32(s.log_betas, i)
     frac = (var_values + 1) / 2
     log_var = frac * max_log + (1 - frac) * min_log
-    x0 = _f32(s.sqrt_alphas_cumprod, i) * x - _f32(s.sqrt_one_minus_alphas_cumprod, i) * v
+    if parameterization == "v":
+        x0 = _f32(s.sqrt_alphas_cumprod, i) * x - _f32(s.sqrt_one_minus_alphas_cumprod, i) * v
+    elif parameterization == "eps":
+        x0 = _f32(s.sqrt_recip_alphas_cumprod, i) * x - _f32(s.sqrt_recipm1_alphas_cumprod, i) * v
+    elif parameterization == "xstart":
+        x0 = v
+    else:
+        raise NotImplementedError(parameterization)
     if clip_denoised:
         x0 = x0.clamp(-1, 1)
     mean = _f32(s.posterior_mean_coef1, i) * x0 + _f32(s.posterior_mean_coef2, i) * x
     return {"mean": mean, "log_variance": log_var, "pred_xstart": x0}
 
 
-def ddim_step(s: Schedule, x, model_out, i: int, eta: float = 0.0, noise=None, clip_denoised=False):
+def ddim_step(s: Schedule, x, model_out, i: int, eta: float = 0.0, noise=None, clip_denoised=False, parameterization="v"):
     """ddim_sample (gaussian_diffusion.py:531-578)."""
-    out = predict(s, x, model_out, i, clip_denoised)
+    out = predict(s, x, model_out, i, clip_denoised, parameterization)
     x0 = out["pred_xstart"]
     eps = (_f32(s.sqrt_recip_alphas_cumprod, i) * x - x0) / _f32(s.sqrt_recipm1_alphas_cumprod, i)
     ab, abp = _f32(s.alphas_cumprod, i), _f32(s.alphas_cumprod_prev, i)
@@ -118,15 +127,15 @@ def ddim_step(s: Schedule, x, model_out, i: int, eta: float = 0.0, noise=None, c
     return {"sample": sample, "pred_xstart": x0}
 
 
-def ddpm_step(s: Schedule, x, model_out, i: int, noise, clip_denoised=False):
+def ddpm_step(s: Schedule, x, model_out, i: int, noise, clip_denoised=False, parameterization="v"):
     """p_sample (gaussian_diffusion.py:397-440)."""
-    out = predict(s, x, model_out, i, clip_denoised)
+    out = predict(s, x, model_out, i, clip_denoised, parameterization)
     sample = out["mean"] + (0.0 if i == 0 else 1.0) * torch.exp(0.5 * out["log_variance"]) * noise
     return {"sample": sample, "pred_xstart": out["pred_xstart"]}
 
 
 def sample_loop(s: Schedule, model: Callable, noise: torch.Tensor, ddim: bool = True, eta: float = 0.0,
-                clip_denoised: bool = False, step_noise: Callable | None = None) -> Iterator[Dict[str, torch.Tensor]]:
+                clip_denoised: bool = False, step_noise: Callable | None = None, parameterization: str = "v") -> Iterator[Dict[str, torch.Tensor]]:
     """ddim_sample_loop_progressive / p_sample_loop_progressive.  ``model(x, t_orig)`` receives the
     ORIGINAL-schedule timestep (respace.py:124-129), as an int64 tensor of shape [B]."""
     img = noise
@@ -134,6 +143,6 @@ def sample_loop(s: Schedule, model: Callable, noise: torch.Tensor, ddim: bool = 
         t = torch.full((img.shape[0],), s.timestep_map[i], dtype=torch.int64, device=img.device)
         mo = model(img, t).float()
         nz = step_noise(img) if step_noise is not None else torch.zeros_like(img)
-        out = ddim_step(s, img, mo, i, eta, nz, clip_denoised) if ddim else ddpm_step(s, img, mo, i, nz, clip_denoised)
+        out = ddim_step(s, img, mo, i, eta, nz, clip_denoised, parameterization) if ddim else ddpm_step(s, img, mo, i, nz, clip_denoised, parameterization)
         yield out
         img = out["sample"]

@@ -92,8 +92,9 @@ def test_schedule_matches_reference_fixture(golden_dir):
     dl = tpxl_b200.create_diffusion("ddim50", noise_schedule="linear", diffusion_steps=1000, parameterization="v")
     assert np.array_equal(np.array(dl.timestep_map), g["map_linear_ddim50"])
     np.testing.assert_allclose(dl.alphas_cumprod, g["acp_linear_ddim50"], rtol=1e-12)
+    assert tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2").parameterization == "eps"      # the reference's default argument (__init__.py:14)
     with pytest.raises(NotImplementedError):
-        tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="eps")
+        tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="v", learn_sigma=False)   # fixed variances: C-channel model output
     with pytest.raises(NotImplementedError):
         tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization="bogus")
     with pytest.raises(ValueError):
@@ -136,6 +137,30 @@ def test_host_coefficients_and_update_order_reproduce_the_reference_with_clip(go
         eps = ((f(k.sqrt_recip_ab) * x - x0) / f(k.sqrt_recipm1_ab)).astype(f)
         x = (x0 * f(k.c_x0) + f(k.c_eps) * eps).astype(f)
         assert np.array_equal(x0, g["ddim25_x0"][n]) and np.array_equal(x, g["ddim25_samples"][n]), n
+
+
+@pytest.mark.parametrize("par", ["eps", "xstart"])
+@pytest.mark.parametrize("clip", [False, True])
+def test_eps_and_xstart_parameterisations_reproduce_the_reference_bit_for_bit(golden_dir, par, clip):
+    """create_diffusion's other parameterisations ("eps" is the reference's default argument) reach the SAME update kernel through the
+    host coefficients alone (pred_xstart = a x_t - b out with per-step (a, b), SpacedDiffusion.step_coefs).  The kernel's op order in
+    numpy float32 on those coefficients reproduces the reference sampler's 25-step DDIM trajectory bit for bit (fixture: the reference's
+    own sampler on replayed model outputs, tests/golden/make_sampler_param_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "sampler_param.npz"))
+    d = tpxl_b200.create_diffusion("ddim25", "squaredcos_cap_v2", parameterization=par)
+    f = np.float32
+    x = g["x_T"].copy()
+    tag = f"{par}_ddim25" + ("_clip" if clip else "")
+    with np.errstate(over="ignore", invalid="ignore"):
+        for n, i in enumerate(reversed(range(25))):
+            k = d.step_coefs(i, 0.0, clip)
+            v = g["outs25"][n][..., :68]
+            x0 = (f(k.sqrt_ab) * x - f(k.sqrt_1mab) * v).astype(f)
+            if clip:
+                x0 = np.minimum(np.maximum(x0, f(-1)), f(1))
+            eps = ((f(k.sqrt_recip_ab) * x - x0) / f(k.sqrt_recipm1_ab)).astype(f)
+            x = (x0 * f(k.c_x0) + f(k.c_eps) * eps).astype(f)
+            assert np.array_equal(x0, g[tag + "_x0"][n]) and np.array_equal(x, g[tag + "_samples"][n]), n
 
 
 def test_state_dict_contract_on_host(golden_dir):

@@ -234,3 +234,21 @@ def test_clip_denoised_loop_reproduces_the_reference_fixture(golden_dir):
         assert float(o["pred_xstart"].abs().max()) <= 1.0
         assert rel_l2(o["pred_xstart"], torch.from_numpy(g["ddim25_x0"][i]).to(DEV)) < 1e-5, i
         assert rel_l2(o["sample"], torch.from_numpy(g["ddim25_samples"][i]).to(DEV)) < 1e-5, i
+
+
+@pytest.mark.parametrize("par,clip", [("eps", False), ("eps", True), ("xstart", False), ("xstart", True)])
+def test_eps_and_xstart_parameterisations_reproduce_the_reference_fixture(golden_dir, par, clip):
+    """create_diffusion(parameterization="eps" | "xstart") ("eps" is the reference's default argument): the same update kernel with other
+    host coefficients.  Seeded model outputs replayed through the REFERENCE sampler on the CPU are the fixture
+    (tests/golden/make_sampler_param_golden.py); replayed through this package's CUDA loop they must give the same 25 samples."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "sampler_param.npz"))
+    x_T = torch.from_numpy(g["x_T"]).to(DEV)
+    outs = iter(torch.from_numpy(g["outs25"]).to(DEV))
+    d = tpxl_b200.create_diffusion("ddim25", noise_schedule="squaredcos_cap_v2", diffusion_steps=1000, parameterization=par)
+    traj = list(d.ddim_sample_loop_progressive(lambda x, t, **kw: next(outs), tuple(x_T.shape), x_T, clip_denoised=clip, model_kwargs={}, progress=False, device=DEV))
+    tag = f"{par}_ddim25" + ("_clip" if clip else "")
+    for i, o in enumerate(traj):
+        assert rel_l2(o["pred_xstart"], torch.from_numpy(g[tag + "_x0"][i]).to(DEV)) < 1e-5, i
+        assert rel_l2(o["sample"], torch.from_numpy(g[tag + "_samples"][i]).to(DEV)) < 1e-5, i

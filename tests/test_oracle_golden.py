@@ -153,6 +153,31 @@ def test_sampler_with_clip_denoised_matches_reference(golden_dir):
     assert _rel(plain[0]["pred_xstart"], g["ddim25_x0"][0]) > 1e-2
 
 
+@pytest.mark.parametrize("par", ["eps", "xstart"])
+def test_sampler_eps_and_xstart_parameterisations_match_reference(golden_dir, par):
+    """The oracle under create_diffusion's other parameterisations against the reference sampler on replayed model outputs
+    (tests/golden/make_sampler_param_golden.py): 25-step DDIM with and without the clamp, 10-step DDPM."""
+    g = _load(golden_dir, "sampler_param.npz")
+    x_T = torch.from_numpy(g["x_T"])
+
+    def replay(outs):
+        it = iter(torch.from_numpy(outs))
+        return lambda xx, tt: next(it)
+
+    s25, s10 = oracle.diffusion.Schedule("ddim25"), oracle.diffusion.Schedule("10")
+    for clip in (False, True):
+        tag = f"{par}_ddim25" + ("_clip" if clip else "")
+        traj = list(oracle.diffusion.sample_loop(s25, replay(g["outs25"]), x_T, ddim=True, clip_denoised=clip, parameterization=par))
+        for i, o in enumerate(traj):
+            assert _rel(o["pred_xstart"], g[tag + "_x0"][i]) < 1e-6 and _rel(o["sample"], g[tag + "_samples"][i]) < 1e-6, (clip, i)
+    torch.manual_seed(21)
+    traj = list(oracle.diffusion.sample_loop(s10, replay(g["outs10"]), x_T, ddim=False, step_noise=torch.randn_like, parameterization=par))
+    assert max(_rel(o["sample"], g[f"{par}_ddpm10_samples"][i]) for i, o in enumerate(traj)) < 1e-6
+    other = "xstart" if par == "eps" else "eps"          # the fixture tells the parameterisations apart
+    wrong = list(oracle.diffusion.sample_loop(s25, replay(g["outs25"]), x_T, ddim=True, parameterization=other))
+    assert _rel(wrong[0]["sample"], g[f"{par}_ddim25_samples"][0]) > 1e-2
+
+
 def test_vae_decode_matches_reference(golden_dir):
     g = _load(golden_dir, "vae_decode.npz")
     sd = synth.synth_state_dict(synth.vae_decoder_shapes(**synth.FULL_VAE), 103)
