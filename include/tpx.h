@@ -105,9 +105,12 @@ int tpx_dit_forward_step(tpx_dit* h, const float* x_dev, int64_t t, int B, int u
 int tpx_dit_debug_residual(const tpx_dit* h, const void* ws, int n_seq, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Sampler update — models/diffusion/gaussian_diffusion.py:255-338 (p_mean_variance, VELOCITY + LEARNED_RANGE),
+ * Sampler update — models/diffusion/gaussian_diffusion.py:255-338 (p_mean_variance, LEARNED_RANGE variance),
  * :531-578 (ddim_sample), :397-440 (p_sample).  Coefficients are the float64 tables evaluated at the step and
  * rounded to fp32 exactly like _extract_into_tensor (:880-892); the host mirror computes them.
+ * pred_xstart = sqrt_ab * x - sqrt_1mab * model_out (one rounding per op): with (sqrt(ab), sqrt(1-ab)) this is VELOCITY (:340-344, the
+ * released model), with (sqrt(1/ab), sqrt(1/ab-1)) EPSILON (:346-351), with (0, -1) START_X (:319-320); clip != 0 clamps it to [-1, 1]
+ * (process_xstart, :310-315).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct tpx_sampler_coefs {
     float sqrt_ab, sqrt_1mab, sqrt_recip_ab, sqrt_recipm1_ab;
