@@ -7,7 +7,9 @@ Workload (BASELINE.json configs[1]): image-conditioned DDIM, CFG 6, 2048 tokens 
 sample per GPU.  A *step* is one `forward_with_cfg` (two sequences) + the sampler update.  Synthetic weights of the
 shipped architecture and synthetic inputs of the shipped shapes (no checkpoints or images exist offline).
 
-  value    steps/s, whole job: inputs already in HBM, device-timed (CUDA events on the launch stream), max over ranks.
+  value    steps/s, whole job: inputs already in HBM, device-timed (CUDA events on the launch stream), max over ranks.  The timestep
+           embedding + adaLN modulation rows of the schedule are computed once per image (DiT.set_timesteps, what the sampling loops do)
+           INSIDE the timed region — every 25 steps — and `timestep_table` reports their cost and the rate without the hoist.
   e2e      the same through the public API from HOST buffers: every step copies x_t from pinned host memory, runs
            forward_with_cfg + the update, and reads x_{t-1} back to pinned host memory; the per-image conditioning
            upload and K/V hoist are inside the timed region too.
