@@ -172,7 +172,7 @@ class SpacedDiffusion:
         ``model.forward``) or as the module itself (``__call__`` -> ``forward``); any wrapper, subclass override or other model is called with
         the reference's arguments only."""
         from .dit import DiT
-        if not self.hoist_timesteps or "t_host" in model_kwargs:
+        if not self.hoist_timesteps or "t_host" in model_kwargs or self.num_timesteps > 4096:      # 4096 = what one table holds (tpx.h)
             return None
         if isinstance(model, DiT):
             owner, target = model, type(model).forward

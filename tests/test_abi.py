@@ -269,6 +269,8 @@ def test_timestep_hoist_is_offered_only_to_this_packages_own_dit_methods():
     assert d._hoist_owner(s.forward_with_cfg, {}) is None and d._hoist_owner(s.forward, {}) is s and d._hoist_owner(s, {}) is s
     d.hoist_timesteps = False
     assert d._hoist_owner(m.forward_with_cfg, {}) is None
+    long = tpxl_b200.create_diffusion("", noise_schedule="linear", diffusion_steps=5000, parameterization="v")   # more steps than a table holds
+    assert long.num_timesteps == 5000 and long._hoist_owner(m.forward_with_cfg, {}) is None
     # the two reference signatures still bind positionally (inference.py:278-280 passes keywords; gaussian_diffusion.py:279 positionals + kwargs)
     import inspect
     for fn in (tpxl_b200.DiT.forward, tpxl_b200.DiT.forward_with_cfg):
